@@ -1,0 +1,278 @@
+"""fp32 CPU restatement of the reference attention forwards (TEST ORACLE).
+
+Every function is functional (weights passed explicitly, names = the
+reference ``state_dict`` keys with dots turned into underscores) and written in
+einsum / explicit-index form, independent of the reference's
+reshape/permute chains, so that an index-path mistake in either side shows up
+as a mismatch.  All math is fp32 (or fp64 when ``dtype=torch.float64``) on CPU.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+
+_F = torch.float32
+
+
+def _lin(x, w, b=None):
+    """y[..., o] = sum_c x[..., c] w[o, c] (+ b[o])  — nn.Linear semantics."""
+    y = torch.einsum("...c,oc->...o", x, w)
+    return y if b is None else y + b
+
+
+def _softmax_last(s):
+    m = s.amax(dim=-1, keepdim=True)
+    e = torch.exp(s - m)
+    return e / e.sum(dim=-1, keepdim=True)
+
+
+def _bn_eval(t, w, b, mean, var, eps):
+    """Eval-mode BatchNorm2d on [B,C,H,W]: per-channel affine of running stats."""
+    inv = torch.rsqrt(var + eps)
+    return (t - mean[None, :, None, None]) * (inv * w)[None, :, None, None] + b[None, :, None, None]
+
+
+# --------------------------------------------------------------------------
+# ViT  (reference: vision_transformers/ViT.py:67-89; setr.py:50-72 and
+# moat.py:62-84 are the same math)
+# --------------------------------------------------------------------------
+def vit_attention(x, qkv_weight, qkv_bias, proj_weight, proj_bias, num_heads, scale=None):
+    """ViT.Attention.forward (ViT.py:79-89).
+
+    x [B,N,C].  Row o of qkv_weight maps to (s,h,d) = (o//C, (o%C)//hd, o%hd)
+    (the reshape(B,N,3,H,hd) at ViT.py:81).
+    """
+    B, N, C = x.shape
+    H = num_heads
+    hd = C // H
+    scale = hd ** -0.5 if scale is None else scale
+    w = qkv_weight.reshape(3, H, hd, C)
+    qkv = torch.einsum("bnc,shdc->sbhnd", x, w)
+    if qkv_bias is not None:
+        qkv = qkv + qkv_bias.reshape(3, 1, H, 1, hd)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    s = torch.einsum("bhnd,bhmd->bhnm", q, k) * scale          # ViT.py:83
+    p = _softmax_last(s)                                        # ViT.py:84
+    o = torch.einsum("bhnm,bhmd->bnhd", p, v).reshape(B, N, C)  # ViT.py:86
+    return _lin(o, proj_weight, proj_bias)                      # ViT.py:87
+
+
+# --------------------------------------------------------------------------
+# PVT spatial-reduction attention (reference: vision_transformers/pvt.py:52-91)
+# --------------------------------------------------------------------------
+def pvt_attention(x, H_img, W_img, q_weight, q_bias, k_weight, k_bias, v_weight, v_bias,
+                  proj_weight, proj_bias, num_heads, sr_ratio=1,
+                  sr_0_weight=None, sr_0_bias=None, sr_1_weight=None, sr_1_bias=None,
+                  sr_1_running_mean=None, sr_1_running_var=None, bn_eps=1e-5):
+    """pvt.Attention.forward(x, H, W) (pvt.py:73-91), eval-mode BatchNorm.
+
+    K/V tokens: x_[b, i*(W/sr)+j, c] = BN_c( sum_{u,v<sr} w[c,0,u,v] *
+    x[b, (sr*i+u)*W + (sr*j+v), c] + bias[c] )   (pvt.py:77-78).
+    """
+    B, N, C = x.shape
+    nh = num_heads
+    hd = C // nh
+    scale = hd ** -0.5
+    q = _lin(x, q_weight, q_bias).reshape(B, N, nh, hd)
+    if sr_ratio > 1:
+        sr = sr_ratio
+        Hs, Ws = H_img // sr, W_img // sr
+        # image view of the tokens: xi[b, i, u, j, v, c]
+        xi = x.reshape(B, H_img, W_img, C)[:, : Hs * sr, : Ws * sr].reshape(B, Hs, sr, Ws, sr, C)
+        t = torch.einsum("biujvc,cuv->bcij", xi, sr_0_weight[:, 0])
+        t = t + sr_0_bias[None, :, None, None]
+        t = _bn_eval(t, sr_1_weight, sr_1_bias, sr_1_running_mean, sr_1_running_var, bn_eps)
+        kv_in = t.reshape(B, C, Hs * Ws).permute(0, 2, 1)   # [B, M, C]
+    else:
+        kv_in = x
+    M = kv_in.shape[1]
+    k = _lin(kv_in, k_weight, k_bias).reshape(B, M, nh, hd)
+    v = _lin(kv_in, v_weight, v_bias).reshape(B, M, nh, hd)
+    s = torch.einsum("bnhd,bmhd->bhnm", q, k) * scale
+    p = _softmax_last(s)
+    o = torch.einsum("bhnm,bmhd->bnhd", p, v).reshape(B, N, C)
+    return _lin(o, proj_weight, proj_bias)
+
+
+# --------------------------------------------------------------------------
+# CvT convolutional-projection attention (reference: cvt.py:48-76)
+# --------------------------------------------------------------------------
+def _dwconv_same(x, w, b, ks):
+    """Depthwise ks x ks conv, stride 1, zero pad (ks-1)//2, on [B,C,H,W]."""
+    B, C, H, W = x.shape
+    pad = (ks - 1) // 2
+    xp = torch.zeros(B, C, H + 2 * pad, W + 2 * pad, dtype=x.dtype)
+    xp[:, :, pad:pad + H, pad:pad + W] = x
+    out = torch.zeros(B, C, H + 2 * pad - ks + 1, W + 2 * pad - ks + 1, dtype=x.dtype)
+    Ho, Wo = out.shape[2], out.shape[3]
+    for u in range(ks):
+        for v in range(ks):
+            out = out + xp[:, :, u:u + Ho, v:v + Wo] * w[None, :, 0, u, v, None, None]
+    return out + b[None, :, None, None]
+
+
+def cvt_attention(x, conv_proj_qkv_0_weight, conv_proj_qkv_0_bias,
+                  conv_proj_qkv_1_weight, conv_proj_qkv_1_bias,
+                  conv_proj_qkv_1_running_mean, conv_proj_qkv_1_running_var,
+                  conv_proj_qkv_2_weight, conv_proj_qkv_2_bias,
+                  proj_weight, proj_bias, num_heads, ks=3, bn_eps=1e-5):
+    """cvt.Attention.forward (cvt.py:64-76).  x and result are NCHW.
+
+    out-channel o of the 1x1 qkv conv maps to (s,h,d)=(o//C,(o%C)//hd,o%hd)
+    (reshape(B,3,H,hd,Hh,Ww) at cvt.py:66); tokens n = r*W + c.
+    """
+    B, C, Hh, Ww = x.shape
+    nh = num_heads
+    hd = C // nh
+    scale = hd ** -0.5
+    t = _dwconv_same(x, conv_proj_qkv_0_weight, conv_proj_qkv_0_bias, ks)
+    t = _bn_eval(t, conv_proj_qkv_1_weight, conv_proj_qkv_1_bias,
+                 conv_proj_qkv_1_running_mean, conv_proj_qkv_1_running_var, bn_eps)
+    t = t.reshape(B, C, Hh * Ww)
+    w = conv_proj_qkv_2_weight.reshape(3, nh, hd, C)
+    qkv = torch.einsum("bcn,shdc->sbhnd", t, w) + conv_proj_qkv_2_bias.reshape(3, 1, nh, 1, hd)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    s = torch.einsum("bhnd,bhmd->bhnm", q, k) * scale
+    p = _softmax_last(s)
+    o = torch.einsum("bhnm,bhmd->bhdn", p, v).reshape(B, C, Hh * Ww)   # channel = h*hd+d
+    y = torch.einsum("bcn,oc->bon", o, proj_weight.reshape(C, C)) + proj_bias[None, :, None]
+    return y.reshape(B, C, Hh, Ww)
+
+
+# --------------------------------------------------------------------------
+# CSWin (reference: cswin.py:51-127, 130-197, 199-216)
+# --------------------------------------------------------------------------
+def _cswin_window_shape(resolution, idx, split_size):
+    if idx == -1:
+        return resolution, resolution
+    if idx == 0:
+        return resolution, split_size
+    if idx == 1:
+        return split_size, resolution
+    raise ValueError(f"ERROR MODE {idx}")   # reference prints and exit(0)s, cswin.py:68-70
+
+
+def cswin_window_table(resolution, idx, split_size):
+    """Integer index path of img2windows/windows2img (cswin.py:199-216).
+
+    Returns int64 array T[nwin, H_sp*W_sp]: image-token index (r*W+c) of token t
+    of window w, with window id i*(W/W_sp)+j and in-window index r*W_sp+c.
+    """
+    H = W = resolution
+    H_sp, W_sp = _cswin_window_shape(resolution, idx, split_size)
+    nI, nJ = H // H_sp, W // W_sp
+    T = np.empty((nI * nJ, H_sp * W_sp), dtype=np.int64)
+    for i in range(nI):
+        for j in range(nJ):
+            for r in range(H_sp):
+                for c in range(W_sp):
+                    T[i * nJ + j, r * W_sp + c] = (i * H_sp + r) * W + (j * W_sp + c)
+    return T
+
+
+def cswin_lepe_attention(qkv, get_v_weight, get_v_bias, resolution, idx, split_size,
+                         num_heads, scale=None):
+    """LePEAttention.forward (cswin.py:101-127).  qkv [3,B,L,C'] -> [B,L,C']."""
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    B, L, C = q.shape
+    H = W = resolution
+    assert L == H * W, "flatten img_tokens has wrong size"
+    H_sp, W_sp = _cswin_window_shape(resolution, idx, split_size)
+    nh = num_heads
+    hd = C // nh
+    scale = hd ** -0.5 if scale is None else scale
+    T = torch.from_numpy(cswin_window_table(resolution, idx, split_size))   # [nw, Nw]
+    nw, Nw = T.shape
+    qw = q[:, T].reshape(B, nw, Nw, nh, hd)
+    kw = k[:, T].reshape(B, nw, Nw, nh, hd)
+    vw = v[:, T].reshape(B, nw, Nw, nh, hd)
+    s = torch.einsum("bwnhd,bwmhd->bwhnm", qw * scale, kw)          # cswin.py:116-117
+    p = _softmax_last(s)
+    o = torch.einsum("bwhnm,bwmhd->bwnhd", p, vw)
+    # LePE: depthwise 3x3 over each window, zero padded at window borders (cswin.py:93-96)
+    vimg = vw.reshape(B * nw, H_sp, W_sp, C).permute(0, 3, 1, 2)
+    lepe = _dwconv_same(vimg, get_v_weight, get_v_bias, 3)          # [B*nw, C, H_sp, W_sp]
+    lepe = lepe.permute(0, 2, 3, 1).reshape(B, nw, Nw, nh, hd)
+    o = (o + lepe).reshape(B, nw * Nw, C)
+    out = torch.empty(B, L, C, dtype=o.dtype)
+    out[:, T.reshape(-1)] = o                                        # windows2img, cswin.py:208-216
+    return out
+
+
+def _layer_norm(x, w, b, eps=1e-5):
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    return (x - mu) * torch.rsqrt(var + eps) * w + b
+
+
+def cswin_block_attention(x, norm1_weight, norm1_bias, qkv_weight, qkv_bias,
+                          proj_weight, proj_bias, get_v_weights, get_v_biases,
+                          reso, num_heads, split_size=7, last_stage=False,
+                          qk_scale=None, residual=True):
+    """Attention half of CSWinBlock.forward (cswin.py:176-194).
+
+    get_v_weights/biases: list over branches (attns.{i}.get_v.*).  Returns
+    x + proj(cat(branches)) if ``residual`` else proj(cat(branches)).
+    """
+    B, L, C = x.shape
+    assert L == reso * reso, "flatten img_tokens has wrong size"
+    if reso == split_size:
+        last_stage = True
+    img = _layer_norm(x, norm1_weight, norm1_bias)
+    qkv = _lin(img, qkv_weight, qkv_bias).reshape(B, L, 3, C).permute(2, 0, 1, 3)   # o -> (s, c)
+    if last_stage:
+        att = cswin_lepe_attention(qkv, get_v_weights[0], get_v_biases[0], reso, -1, split_size,
+                                   num_heads, qk_scale)
+    else:
+        half = C // 2
+        a0 = cswin_lepe_attention(qkv[..., :half], get_v_weights[0], get_v_biases[0], reso, 0,
+                                  split_size, num_heads // 2, qk_scale)
+        a1 = cswin_lepe_attention(qkv[..., half:], get_v_weights[1], get_v_biases[1], reso, 1,
+                                  split_size, num_heads // 2, qk_scale)
+        att = torch.cat([a0, a1], dim=2)
+    y = _lin(att, proj_weight, proj_bias)
+    return x + y if residual else y
+
+
+# --------------------------------------------------------------------------
+# XCiT (reference: xcit.py:159-188, 233-265)
+# --------------------------------------------------------------------------
+def xca_attention(x, qkv_weight, qkv_bias, proj_weight, proj_bias, temperature, num_heads):
+    """XCA.forward (xcit.py:245-265): channel x channel attention."""
+    B, N, C = x.shape
+    H = num_heads
+    hd = C // H
+    w = qkv_weight.reshape(3, H, hd, C)
+    qkv = torch.einsum("bnc,shdc->sbhdn", x, w)       # already [.., hd, N] (xcit.py:251-253)
+    if qkv_bias is not None:
+        qkv = qkv + qkv_bias.reshape(3, 1, H, hd, 1)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    qn = q / q.norm(dim=-1, keepdim=True).clamp_min(1e-12)      # F.normalize, xcit.py:255
+    kn = k / k.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    a = torch.einsum("bhdn,bhen->bhde", qn, kn) * temperature.reshape(1, H, 1, 1)
+    a = _softmax_last(a)
+    o = torch.einsum("bhde,bhen->bnhd", a, v).reshape(B, N, C)  # xcit.py:262
+    return _lin(o, proj_weight, proj_bias)
+
+
+def class_attention(x, qkv_weight, qkv_bias, proj_weight, proj_bias, num_heads, scale=None):
+    """ClassAttention.forward (xcit.py:174-188): CLS query only; patch tokens pass through."""
+    B, N, C = x.shape
+    H = num_heads
+    hd = C // H
+    scale = hd ** -0.5 if scale is None else scale
+    w = qkv_weight.reshape(3, H, hd, C)
+    qkv = torch.einsum("bnc,shdc->sbhnd", x, w)
+    if qkv_bias is not None:
+        qkv = qkv + qkv_bias.reshape(3, 1, H, 1, hd)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    a = torch.einsum("bhd,bhnd->bhn", q[:, :, 0], k) * scale     # xcit.py:180-181
+    a = _softmax_last(a)
+    cls = torch.einsum("bhn,bhnd->bhd", a, v).reshape(B, 1, C)   # xcit.py:185
+    cls = _lin(cls, proj_weight, proj_bias)
+    return torch.cat([cls, x[:, 1:]], dim=1)                     # xcit.py:187

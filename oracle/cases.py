@@ -1,0 +1,170 @@
+"""Case definitions shared by the golden generator and the tests (TEST ORACLE).
+
+A *spec* is a plain dict: {"variant", "ctor": {...}, "x": shape tuple, extra}.
+``params`` are always ``state_dict`` tensors keyed by the reference's own keys.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+
+import torch
+
+from . import attention as A
+
+GOLDEN_CASES = {
+    # ViT.Attention(dim, num_heads, qkv_bias)            ViT.py:67-89
+    "vit_b2_n197_c128_h2": dict(variant="vit", ctor=dict(dim=128, num_heads=2), x=(2, 197, 128)),
+    "vit_b3_n50_c192_h3_bias": dict(variant="vit", ctor=dict(dim=192, num_heads=3, qkv_bias=True), x=(3, 50, 192)),
+    # pvt.Attention(dim, num_heads, sr_ratio)            pvt.py:52-91
+    "pvt_b2_16x16_c128_h2_sr4": dict(variant="pvt", ctor=dict(dim=128, num_heads=2, sr_ratio=4), x=(2, 256, 128), hw=(16, 16)),
+    "pvt_b2_8x8_c128_h2_sr1_bias": dict(variant="pvt", ctor=dict(dim=128, num_heads=2, sr_ratio=1, qkv_bias=True), x=(2, 64, 128), hw=(8, 8)),
+    # cvt.Attention(dim, num_heads, ks)                   cvt.py:48-76
+    "cvt_b2_c128_h2_14x14": dict(variant="cvt", ctor=dict(dim=128, num_heads=2), x=(2, 128, 14, 14)),
+    # cswin.LePEAttention(dim, resolution, idx, split_size, num_heads)   cswin.py:51-127
+    "lepe_b2_c64_h2_r14_idx0": dict(variant="lepe", ctor=dict(dim=64, resolution=14, idx=0, split_size=7, num_heads=2), x=(3, 2, 196, 64)),
+    "lepe_b2_c64_h2_r14_idx1": dict(variant="lepe", ctor=dict(dim=64, resolution=14, idx=1, split_size=7, num_heads=2), x=(3, 2, 196, 64)),
+    "lepe_b2_c64_h2_r7_idxm1": dict(variant="lepe", ctor=dict(dim=64, resolution=7, idx=-1, split_size=7, num_heads=2), x=(3, 2, 49, 64)),
+    # cswin.CSWinBlock attention half                      cswin.py:130-194
+    "cswinblk_b2_c128_r14_h4": dict(variant="cswin_block", ctor=dict(dim=128, reso=14, num_heads=4, split_size=7, qkv_bias=True), x=(2, 196, 128)),
+    "cswinblk_b2_c128_r7_h4_last": dict(variant="cswin_block", ctor=dict(dim=128, reso=7, num_heads=4, split_size=7, qkv_bias=True, last_stage=True), x=(2, 49, 128)),
+    # xcit.XCA / xcit.ClassAttention                       xcit.py:233-265, 159-188
+    "xca_b2_n196_c128_h2": dict(variant="xca", ctor=dict(dim=128, num_heads=2, qkv_bias=True), x=(2, 196, 128)),
+    "classattn_b2_n197_c128_h2": dict(variant="class_attn", ctor=dict(dim=128, num_heads=2, qkv_bias=True), x=(2, 197, 128)),
+}
+
+_REF_CLASS = {
+    "vit": ("ViT", "Attention"),
+    "pvt": ("pvt", "Attention"),
+    "cvt": ("cvt", "Attention"),
+    "lepe": ("cswin", "LePEAttention"),
+    "cswin_block": ("cswin", "CSWinBlock"),
+    "xca": ("xcit", "XCA"),
+    "class_attn": ("xcit", "ClassAttention"),
+}
+
+
+def round_fp16_(t):
+    """Round a float tensor in place to fp16-representable values."""
+    if t.is_floating_point():
+        t.copy_(t.half().float())
+    return t
+
+
+def randomise_module_(mod, seed):
+    """Randomise BN stats/affine, LayerNorm affine and XCA temperature:
+    a freshly constructed BN is ~identity and would hide bugs."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, m in mod.named_modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 1.5 + 0.5)
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g))
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g))
+            if isinstance(m, torch.nn.LayerNorm):
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+        for name, p in mod.named_parameters():
+            if name.endswith("temperature"):
+                p.copy_(torch.rand(p.shape, generator=g) * 1.5 + 0.5)
+            if name.endswith(".bias") and "norm" not in name and "sr.1" not in name and "qkv.1" not in name:
+                # default Linear/Conv biases are tiny; widen them a bit so a dropped bias is visible
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+        for p in mod.parameters():
+            round_fp16_(p)
+        for b in mod.buffers():
+            round_fp16_(b)
+    return mod
+
+
+def make_inputs(spec, seed=0):
+    g = torch.Generator().manual_seed(1000 + seed)
+    x = torch.randn(spec["x"], generator=g)
+    return {"x": round_fp16_(x)}
+
+
+def load_reference(ref_path):
+    if ref_path not in sys.path:
+        sys.path.insert(0, ref_path)
+    return {m: importlib.import_module(m) for m in ("ViT", "pvt", "cvt", "cswin", "xcit")}
+
+
+def reference_forward(spec, mod, x):
+    v = spec["variant"]
+    with torch.no_grad():
+        if v == "pvt":
+            return mod(x, *spec["hw"])
+        if v == "cswin_block":
+            # attention half only (cswin.py:184-194): x + proj(attn(norm1(x)))
+            return cswin_block_attention_half_reference(mod, x)
+        return mod(x)
+
+
+def cswin_block_attention_half_reference(blk, x):
+    """Runs the reference CSWinBlock's own sub-modules for lines cswin.py:181-194
+    (everything before the MLP half)."""
+    B, L, C = x.shape
+    img = blk.norm1(x)
+    qkv = blk.qkv(img).reshape(B, -1, 3, C).permute(2, 0, 1, 3)
+    if blk.branch_num == 2:
+        x1 = blk.attns[0](qkv[:, :, :, :C // 2])
+        x2 = blk.attns[1](qkv[:, :, :, C // 2:])
+        att = torch.cat([x1, x2], dim=2)
+    else:
+        att = blk.attns[0](qkv)
+    return x + blk.proj(att)
+
+
+def build_reference_case(spec, ref_path, seed=0):
+    mods = load_reference(ref_path)
+    modname, clsname = _REF_CLASS[spec["variant"]]
+    torch.manual_seed(seed)
+    mod = getattr(mods[modname], clsname)(**spec["ctor"]).eval()
+    randomise_module_(mod, seed + 7)
+    inputs = make_inputs(spec, seed)
+    y = reference_forward(spec, mod, inputs["x"]).float()
+    params = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    return {"inputs": inputs, "params": params, "y_ref": y, "module": mod}
+
+
+def _kw(params, *keys):
+    return {k.replace(".", "_"): params.get(k) for k in keys}
+
+
+def run_oracle_case(spec, inputs, params, dtype=torch.float32):
+    """Evaluate the oracle restatement for a spec.  params: reference state_dict."""
+    v = spec["variant"]
+    c = spec["ctor"]
+    P = {k: (t.to(dtype) if t.is_floating_point() else t) for k, t in params.items()}
+    x = inputs["x"].to(dtype)
+    if v == "vit":
+        return A.vit_attention(x, P["qkv.weight"], P.get("qkv.bias"), P["proj.weight"], P["proj.bias"],
+                               c["num_heads"])
+    if v == "pvt":
+        kw = _kw(P, "q.weight", "q.bias", "k.weight", "k.bias", "v.weight", "v.bias", "proj.weight", "proj.bias",
+                 "sr.0.weight", "sr.0.bias", "sr.1.weight", "sr.1.bias", "sr.1.running_mean", "sr.1.running_var")
+        return A.pvt_attention(x, spec["hw"][0], spec["hw"][1], num_heads=c["num_heads"],
+                               sr_ratio=c.get("sr_ratio", 1), **kw)
+    if v == "cvt":
+        kw = _kw(P, "conv_proj_qkv.0.weight", "conv_proj_qkv.0.bias", "conv_proj_qkv.1.weight",
+                 "conv_proj_qkv.1.bias", "conv_proj_qkv.1.running_mean", "conv_proj_qkv.1.running_var",
+                 "conv_proj_qkv.2.weight", "conv_proj_qkv.2.bias", "proj.weight", "proj.bias")
+        return A.cvt_attention(x, num_heads=c["num_heads"], ks=c.get("ks", 3), **kw)
+    if v == "lepe":
+        return A.cswin_lepe_attention(x, P["get_v.weight"], P["get_v.bias"], c["resolution"], c["idx"],
+                                      c.get("split_size", 7), c["num_heads"], c.get("qk_scale"))
+    if v == "cswin_block":
+        nb = 1 if (c.get("last_stage", False) or c["reso"] == c.get("split_size", 7)) else 2
+        return A.cswin_block_attention(
+            x, P["norm1.weight"], P["norm1.bias"], P["qkv.weight"], P.get("qkv.bias"),
+            P["proj.weight"], P["proj.bias"],
+            [P[f"attns.{i}.get_v.weight"] for i in range(nb)], [P[f"attns.{i}.get_v.bias"] for i in range(nb)],
+            c["reso"], c["num_heads"], c.get("split_size", 7), c.get("last_stage", False), c.get("qk_scale"))
+    if v == "xca":
+        return A.xca_attention(x, P["qkv.weight"], P.get("qkv.bias"), P["proj.weight"], P["proj.bias"],
+                               P["temperature"], c["num_heads"])
+    if v == "class_attn":
+        return A.class_attention(x, P["qkv.weight"], P.get("qkv.bias"), P["proj.weight"], P["proj.bias"],
+                                 c["num_heads"], c.get("qk_scale"))
+    raise KeyError(v)

@@ -1,0 +1,35 @@
+"""Whenever the live reference is mounted (build container), re-check the oracle and the
+index paths against it directly, on fresh seeds and on arange tensors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.cases import GOLDEN_CASES, build_reference_case, run_oracle_case, load_reference
+from oracle import cswin_window_table
+
+REF = os.environ.get("PA_REFERENCE", "/root/reference/vision_transformers")
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted (GPU box)")
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+@pytest.mark.parametrize("seed", [1, 2])
+def test_oracle_vs_live_reference(name, seed):
+    spec = GOLDEN_CASES[name]
+    case = build_reference_case(spec, REF, seed=seed)
+    y = run_oracle_case(spec, case["inputs"], case["params"])
+    tol = 5e-6 * max(1.0, case["y_ref"].abs().max().item())
+    assert (y - case["y_ref"]).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("reso,idx,split", [(14, 0, 7), (14, 1, 7), (7, -1, 7), (28, 0, 2)])
+def test_window_table_vs_reference_img2windows(reso, idx, split):
+    """Push an arange image through the reference's img2windows: bit-exact index table."""
+    cswin = load_reference(REF)["cswin"]
+    H_sp, W_sp = {(-1): (reso, reso), 0: (reso, split), 1: (split, reso)}[idx]
+    img = torch.arange(reso * reso, dtype=torch.float32).reshape(1, 1, reso, reso)
+    win = cswin.img2windows(img, H_sp, W_sp)[..., 0].long().numpy()
+    assert np.array_equal(win, cswin_window_table(reso, idx, split))
+    back = cswin.windows2img(torch.from_numpy(win).float().reshape(-1, H_sp, W_sp, 1), H_sp, W_sp, reso, reso)
+    assert np.array_equal(back.reshape(-1).long().numpy(), np.arange(reso * reso))
