@@ -1,0 +1,99 @@
+/* pa_b200.h — C ABI of the B200-native attention-forward library (libpa_b200.so).
+ *
+ * Drop-in boundary for the multi-head self-attention forward that recurs in the reference
+ * (changzy00/pytorch-attention, vision_transformers/):
+ *     ViT.Attention.forward            ViT.py:79-89      -> pa_vit_fwd
+ *     pvt.Attention.forward            pvt.py:73-91      -> pa_pvt_fwd
+ *     cvt.Attention.forward            cvt.py:64-76      -> pa_cvt_fwd
+ *     cswin.LePEAttention.forward      cswin.py:101-127  -> pa_cswin_lepe_fwd
+ *     cswin.CSWinBlock.forward (attn)  cswin.py:176-194  -> pa_cswin_block_attn_fwd
+ *     xcit.XCA.forward                 xcit.py:245-265   -> pa_xca_fwd
+ *     xcit.ClassAttention.forward      xcit.py:174-188   -> pa_class_attn_fwd
+ * The reference has no FFI of its own (it is pure Python calling ATen); these entry points are what a
+ * ctypes binding inside each reference module's forward would call.
+ *
+ * Conventions
+ *   - plain C structs, raw device pointers, sizes, a cudaStream_t passed as void*; no C++/torch types.
+ *   - every function returns 0 on success or a negative PA_ERR_* code; pa_last_error() gives the
+ *     thread-local message.  Nothing is allocated, freed or synchronised by the library: the caller
+ *     owns x, parameters, y and the workspace; launches are asynchronous on the given stream.
+ *   - 16-bit tensors are fp16 or bf16 (PA_DTYPE_*); biases / BN / LN / temperature vectors are fp32.
+ *   - there is NO CPU fallback: on a device that is not compute capability 10.x the calls fail.
+ */
+#ifndef PA_B200_H
+#define PA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PA_VERSION 100
+
+enum { PA_DTYPE_F16 = 0, PA_DTYPE_BF16 = 1, PA_DTYPE_F32 = 2 };
+
+enum {
+  PA_OK = 0,
+  PA_ERR_BAD_SHAPE = -1,      /* dim % heads, head_dim unsupported, L != H*W ... (reference: AssertionError) */
+  PA_ERR_UNSUPPORTED = -2,    /* dtype / mode not implemented on this path */
+  PA_ERR_MISALIGNED = -3,     /* pointer or pitch not 16-byte aligned */
+  PA_ERR_WORKSPACE = -4,      /* workspace missing or too small */
+  PA_ERR_CUDA = -5,           /* CUDA runtime/driver error (message has the cudaError string) */
+  PA_ERR_DEVICE = -6,         /* not an sm_100 device / no device */
+  PA_ERR_NULL = -7            /* required pointer is NULL */
+};
+
+int pa_version(void);
+const char* pa_last_error(void);
+/* 0 if `device` exists and is compute capability 10.x, else PA_ERR_DEVICE. */
+int pa_device_check(int device);
+/* number of kernels this library has launched in the calling process (all threads). */
+unsigned long long pa_launch_count(void);
+
+/* ---------------------------------------------------------------- building blocks (also exported for tests) */
+/* D[z][m,n] = sum_k A[z][m,k] B[z][n,k] (+bias): both operands K-major, i.e. nn.Linear / 1x1-conv layout. */
+typedef struct {
+  int a_dtype, b_dtype, out_dtype;   /* a,b: F16/BF16; out: F16/BF16/F32 */
+  int M, N, K, Z;
+  const void* A; long long lda, a_batch;   /* pitches in elements; a_batch == 0: A shared by all z */
+  const void* B; long long ldb, b_batch;
+  void* D;       long long ldd, d_batch;
+  const float* bias;                 /* fp32, length N (bias_mode 1) or M (bias_mode 2) */
+  int bias_mode;                     /* 0 none, 1 per column, 2 per row */
+  int block_n;                       /* 0 = auto; else 64/96/128/192/256 */
+} pa_gemm_args;
+int pa_gemm_tn(const pa_gemm_args* a, void* stream);
+
+/* O[g][i, h*64+d] = sum_j softmax_j(scale * Q[g][i,h,:].K[g][j,h,:]) V[g][j,h,d];  fp16 in, fp16 out, head_dim 64,
+ * n_k <= 256.  Q rows live in `q` with pitch ldq (elements) and group pitch q_group, head h at column q_col0+64h;
+ * K and V live in one buffer `kv` at columns k_col0+64h / v_col0+64h. */
+typedef struct {
+  int G, H, n_q, n_k;
+  const void* q;  long long ldq, q_group; int q_col0;
+  const void* kv; long long ldkv, kv_group; int k_col0, v_col0;
+  void* o;        long long ldo, o_group;  int o_col0;
+  float scale;
+} pa_attn_args;
+int pa_attn_core(const pa_attn_args* a, void* stream);
+
+/* ---------------------------------------------------------------- ViT.Attention  (ViT.py:67-89) */
+typedef struct {
+  int dtype;                 /* dtype of x and qkv_weight (F16/BF16) */
+  int out_dtype;             /* dtype of y (F16/BF16/F32) */
+  int B, N, C, H;            /* C % H == 0 and C / H == 64 */
+  float scale;               /* head_dim ** -0.5 (ViT.py:73) */
+  const void* x;             /* [B,N,C] contiguous */
+  const void* qkv_weight;    /* [3C,C]  rows ordered (s,h,d), ViT.py:81 */
+  const float* qkv_bias;     /* [3C] fp32 or NULL (qkv_bias=False default, ViT.py:68) */
+  const void* proj_weight;   /* [C,C] fp16 */
+  const float* proj_bias;    /* [C] fp32 or NULL */
+  void* y;                   /* [B,N,C] */
+} pa_vit_args;
+size_t pa_vit_workspace_bytes(const pa_vit_args* a);
+int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PA_B200_H */

@@ -1,0 +1,107 @@
+"""ctypes binding of libpa_b200.so (C ABI in include/pa_b200.h).  No CPU fallback: if the library is missing
+or a call fails, an exception is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+PA_DTYPE_F16, PA_DTYPE_BF16, PA_DTYPE_F32 = 0, 1, 2
+PA_ERR_BAD_SHAPE, PA_ERR_UNSUPPORTED, PA_ERR_MISALIGNED, PA_ERR_WORKSPACE = -1, -2, -3, -4
+PA_ERR_CUDA, PA_ERR_DEVICE, PA_ERR_NULL = -5, -6, -7
+
+_vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("a_dtype", _i), ("b_dtype", _i), ("out_dtype", _i),
+                ("M", _i), ("N", _i), ("K", _i), ("Z", _i),
+                ("A", _vp), ("lda", _ll), ("a_batch", _ll),
+                ("B", _vp), ("ldb", _ll), ("b_batch", _ll),
+                ("D", _vp), ("ldd", _ll), ("d_batch", _ll),
+                ("bias", _vp), ("bias_mode", _i), ("block_n", _i)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [("G", _i), ("H", _i), ("n_q", _i), ("n_k", _i),
+                ("q", _vp), ("ldq", _ll), ("q_group", _ll), ("q_col0", _i),
+                ("kv", _vp), ("ldkv", _ll), ("kv_group", _ll), ("k_col0", _i), ("v_col0", _i),
+                ("o", _vp), ("ldo", _ll), ("o_group", _ll), ("o_col0", _i),
+                ("scale", _f)]
+
+
+class VitArgs(C.Structure):
+    _fields_ = [("dtype", _i), ("out_dtype", _i), ("B", _i), ("N", _i), ("C", _i), ("H", _i),
+                ("scale", _f),
+                ("x", _vp), ("qkv_weight", _vp), ("qkv_bias", _vp), ("proj_weight", _vp), ("proj_bias", _vp),
+                ("y", _vp)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/pa_b200.h must be listed here
+# (tests/test_abi.py cross-checks this table against the header).
+SYMBOLS = {
+    "pa_version": (_i, []),
+    "pa_last_error": (C.c_char_p, []),
+    "pa_device_check": (_i, [_i]),
+    "pa_launch_count": (C.c_ulonglong, []),
+    "pa_gemm_tn": (_i, [C.POINTER(GemmArgs), _vp]),
+    "pa_attn_core": (_i, [C.POINTER(AttnArgs), _vp]),
+    "pa_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitArgs)]),
+    "pa_vit_fwd": (_i, [C.POINTER(VitArgs), _vp, C.c_size_t, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class PaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libpa_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the sources are newer and nvcc is available) and return the CDLL."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if _build.is_stale():
+            try:
+                _build.build_lib()
+            except Exception as e:  # no nvcc, or compile error
+                if not os.path.exists(path):
+                    raise RuntimeError(
+                        f"libpa_b200.so is not built ({path}) and could not be built: {e}. "
+                        "This package has no CPU / PyTorch fallback.") from e
+        lib = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)   # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().pa_last_error()
+        msg = msg.decode() if msg else ""
+        if rc in (PA_ERR_BAD_SHAPE,):
+            raise AssertionError(msg)         # the reference raises AssertionError on shape violations
+        if rc in (PA_ERR_UNSUPPORTED, PA_ERR_MISALIGNED, PA_ERR_NULL, PA_ERR_WORKSPACE):
+            raise ValueError(msg)
+        raise PaError(rc, msg)
+
+
+def launch_count():
+    return int(load().pa_launch_count())

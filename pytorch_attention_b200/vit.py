@@ -1,0 +1,61 @@
+"""Drop-in for ``vision_transformers/ViT.py:Attention`` (reference ViT.py:67-89; the identical math in
+setr.py:50-72 and moat.py:62-84 is covered by the same class)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+from ._common import ParamStage, check_forward_mode, f32, w16
+
+
+class Attention(nn.Module):
+    """Same constructor, ``forward(x[B,N,C]) -> [B,N,C]`` contract and ``state_dict`` keys
+    (``qkv.weight``, [``qkv.bias``], ``proj.weight``, ``proj.bias``) as the reference class (ViT.py:68-77).
+
+    forward = three stream-ordered launches from libpa_b200.so:
+    tcgen05 GEMM (qkv) -> tcgen05/TMEM softmax-attention core -> tcgen05 GEMM (proj)."""
+
+    def __init__(self, dim, num_heads=4, qkv_bias=False, attn_drop=0, proj_drop=0):
+        super().__init__()
+        assert dim % num_heads == 0
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.out_dtype = None          # None: same dtype as x.  torch.float16/float32 selectable (bf16 y cannot meet 1e-3)
+        self._stage = ParamStage()
+
+    def _staged(self, dtype):
+        q, p = self.qkv, self.proj
+        return self._stage.get(
+            ("w", dtype), (q.weight, q.bias, p.weight, p.bias),
+            lambda: (w16(q.weight, dtype), f32(q.bias), w16(p.weight, torch.float16), f32(p.bias)))
+
+    def forward(self, x):
+        check_forward_mode(self, x, (self.attn_drop.p, self.proj_drop.p))
+        B, N, C = x.shape
+        x = x.contiguous()
+        wq, bq, wp, bp = self._staged(x.dtype)
+        y = torch.empty(B, N, C, dtype=self.out_dtype or x.dtype, device=x.device)
+        a = L.VitArgs()
+        a.dtype, a.out_dtype = ops.dtype_code(x.dtype), ops.dtype_code(y.dtype)
+        a.B, a.N, a.C, a.H = B, N, C, self.num_heads
+        a.scale = float(self.scale)
+        a.x, a.qkv_weight, a.qkv_bias = ops._ptr(x), ops._ptr(wq), ops._ptr(bq)
+        a.proj_weight, a.proj_bias, a.y = ops._ptr(wp), ops._ptr(bp), ops._ptr(y)
+        lib = L.load()
+        with torch.cuda.device(x.device):
+            need = lib.pa_vit_workspace_bytes(C.byref(a))
+            if need == 0:   # invalid arguments: let the entry point report the proper error code
+                L.check(lib.pa_vit_fwd(C.byref(a), None, 0, ops.stream_ptr(x.device)))
+            ws = ops.workspace(need, x.device)
+            L.check(lib.pa_vit_fwd(C.byref(a), ops._ptr(ws), ws.numel(), ops.stream_ptr(x.device)))
+        return y
+
