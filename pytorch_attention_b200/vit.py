@@ -2,7 +2,7 @@
 setr.py:50-72 and moat.py:62-84 is covered by the same class)."""
 from __future__ import annotations
 
-import ctypes as C
+import ctypes
 
 import torch
 from torch import nn
@@ -52,10 +52,10 @@ class Attention(nn.Module):
         a.proj_weight, a.proj_bias, a.y = ops._ptr(wp), ops._ptr(bp), ops._ptr(y)
         lib = L.load()
         with torch.cuda.device(x.device):
-            need = lib.pa_vit_workspace_bytes(C.byref(a))
+            need = lib.pa_vit_workspace_bytes(ctypes.byref(a))
             if need == 0:   # invalid arguments: let the entry point report the proper error code
-                L.check(lib.pa_vit_fwd(C.byref(a), None, 0, ops.stream_ptr(x.device)))
+                L.check(lib.pa_vit_fwd(ctypes.byref(a), None, 0, ops.stream_ptr(x.device)))
             ws = ops.workspace(need, x.device)
-            L.check(lib.pa_vit_fwd(C.byref(a), ops._ptr(ws), ws.numel(), ops.stream_ptr(x.device)))
+            L.check(lib.pa_vit_fwd(ctypes.byref(a), ops._ptr(ws), ws.numel(), ops.stream_ptr(x.device)))
         return y
 

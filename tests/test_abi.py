@@ -1,0 +1,69 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol declared in include/pa_b200.h,
+the ctypes table covers the header, and argument validation returns error codes (never crashes)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from pytorch_attention_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "pa_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pa_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound():
+    lib = L.load()
+    names = header_functions()
+    assert "pa_vit_fwd" in names and "pa_gemm_tn" in names
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in pa_b200.h but not exported by libpa_b200.so"
+        assert n in L.SYMBOLS, f"{n} declared in pa_b200.h but missing from the ctypes table"
+    assert sorted(L.SYMBOLS) == names
+
+
+def test_version_and_error_string():
+    lib = L.load()
+    assert lib.pa_version() == 100
+    assert isinstance(lib.pa_last_error(), bytes)
+
+
+def test_vit_argument_validation_without_gpu():
+    lib = L.load()
+    a = L.VitArgs()
+    a.B, a.N, a.C, a.H = 2, 197, 768, 5          # 768 % 5 != 0  (ViT.py:70 assert)
+    assert lib.pa_vit_fwd(C.byref(a), None, 0, None) == L.PA_ERR_BAD_SHAPE
+    assert b"divisible" in lib.pa_last_error()
+    a.H = 6                                       # head_dim 128 unsupported
+    assert lib.pa_vit_fwd(C.byref(a), None, 0, None) == L.PA_ERR_UNSUPPORTED
+    a.H = 12
+    assert lib.pa_vit_workspace_bytes(C.byref(a)) >= 2 * 197 * 768 * 2 * 4
+    assert lib.pa_vit_fwd(C.byref(a), None, 0, None) == L.PA_ERR_NULL   # x/weights NULL
+    assert lib.pa_vit_fwd(None, None, 0, None) == L.PA_ERR_NULL
+
+
+def test_gemm_and_attn_argument_validation_without_gpu():
+    lib = L.load()
+    g = L.GemmArgs()
+    assert lib.pa_gemm_tn(C.byref(g), None) == L.PA_ERR_NULL
+    g.A = g.B = g.D = 16
+    g.M, g.N, g.K, g.Z = 4, 4, 12, 1
+    assert lib.pa_gemm_tn(C.byref(g), None) == L.PA_ERR_BAD_SHAPE      # K % 8
+    at = L.AttnArgs()
+    at.q = at.kv = at.o = 16
+    at.G, at.H, at.n_q, at.n_k, at.scale = 1, 1, 8, 300, 1.0
+    assert lib.pa_attn_core(C.byref(at), None) == L.PA_ERR_UNSUPPORTED  # n_k > 256
+
+
+def test_python_error_mapping():
+    with pytest.raises(AssertionError):
+        L.check(L.PA_ERR_BAD_SHAPE)
+    with pytest.raises(ValueError):
+        L.check(L.PA_ERR_UNSUPPORTED)
+    with pytest.raises(L.PaError):
+        L.check(L.PA_ERR_CUDA)
