@@ -62,11 +62,15 @@ typedef struct {
   const float* bias;                 /* fp32, length N (bias_mode 1) or M (bias_mode 2) */
   int bias_mode;                     /* 0 none, 1 per column, 2 per row */
   int block_n;                       /* 0 = auto; else 64/96/128/192/256 */
+  const void* residual;              /* optional tensor added to the result ([Z][M,N], pitch ldr), or NULL */
+  long long ldr, r_batch;
+  int res_dtype;                     /* F16/BF16/F32 */
 } pa_gemm_args;
 int pa_gemm_tn(const pa_gemm_args* a, void* stream);
 
 /* O[g][i, h*64+d] = sum_j softmax_j(scale * Q[g][i,h,:].K[g][j,h,:]) V[g][j,h,d];  fp16 in, fp16 out, head_dim 64,
- * n_k <= 256.  Q rows live in `q` with pitch ldq (elements) and group pitch q_group, head h at column q_col0+64h;
+ * any n_k
+ * (blocks of keys with an online softmax beyond 256).  Q rows live in `q` with pitch ldq (elements) and group pitch q_group, head h at column q_col0+64h;
  * K and V live in one buffer `kv` at columns k_col0+64h / v_col0+64h. */
 typedef struct {
   int G, H, n_q, n_k;
@@ -74,6 +78,7 @@ typedef struct {
   const void* kv; long long ldkv, kv_group; int k_col0, v_col0;
   void* o;        long long ldo, o_group;  int o_col0;
   float scale;
+  int head_dim;                      /* 0 or 64: 64-wide heads; 32: 32-wide heads */
 } pa_attn_args;
 int pa_attn_core(const pa_attn_args* a, void* stream);
 
@@ -92,6 +97,96 @@ typedef struct {
 } pa_vit_args;
 size_t pa_vit_workspace_bytes(const pa_vit_args* a);
 int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- pvt.Attention  (pvt.py:52-91) */
+typedef struct {
+  int dtype, out_dtype;
+  int B, N, C, H;            /* N == Himg*Wimg, C / H == 64 */
+  int Himg, Wimg, sr;        /* forward(x, H, W) and the constructor's sr_ratio */
+  float scale;
+  const void* x;             /* [B,N,C] */
+  const void* q_weight;      /* [C,C]  (dtype) */
+  const float* q_bias;       /* [C] or NULL */
+  const void* kv_weight;     /* [2C,C] = cat(k.weight, v.weight); fp16 when sr > 1 (its input is the fp16 reduced map), else dtype */
+  const float* kv_bias;      /* [2C] or NULL */
+  const void* proj_weight;   /* [C,C] fp16 */
+  const float* proj_bias;    /* [C] or NULL */
+  const float* sr_weight_t;  /* [sr*sr, C] fp32: sr.0.weight [C,1,sr,sr] transposed (sr > 1) */
+  const float* sr_scale;     /* [C] sr.1.weight * rsqrt(running_var + eps)  (eval BatchNorm folded) */
+  const float* sr_shift;     /* [C] (sr.0.bias - running_mean) * sr_scale + sr.1.bias */
+  void* y;                   /* [B,N,C] */
+} pa_pvt_args;
+size_t pa_pvt_workspace_bytes(const pa_pvt_args* a);
+int pa_pvt_fwd(const pa_pvt_args* a, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- cvt.Attention  (cvt.py:48-76), NCHW in and out */
+typedef struct {
+  int dtype, out_dtype;
+  int B, C, H, Himg, Wimg, ks;
+  float scale;
+  const void* x;             /* [B,C,Himg,Wimg] */
+  const float* dw_weight;    /* [C, ks*ks] fp32  (conv_proj_qkv.0.weight) */
+  const float* dw_scale;     /* [C] BN scale folded */
+  const float* dw_shift;     /* [C] (conv bias - mean) * scale + beta */
+  const void* qkv_weight;    /* [3C,C] fp16 (conv_proj_qkv.2.weight, 1x1) */
+  const float* qkv_bias;     /* [3C] */
+  const void* proj_weight;   /* [C,C] fp16 (proj.weight, 1x1) */
+  const float* proj_bias;    /* [C] */
+  void* y;                   /* [B,C,Himg,Wimg] */
+} pa_cvt_args;
+size_t pa_cvt_workspace_bytes(const pa_cvt_args* a);
+int pa_cvt_fwd(const pa_cvt_args* a, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- xcit.XCA (xcit.py:233-265) and xcit.ClassAttention (xcit.py:159-188) */
+typedef struct {
+  int dtype, out_dtype;
+  int B, N, C, H;            /* C / H == 64 */
+  float scale;               /* ClassAttention only (XCA has no head_dim scale, xcit.py:258) */
+  const void* x;             /* [B,N,C] */
+  const void* qkv_weight;    /* [3C,C] (dtype) */
+  const float* qkv_bias;     /* [3C] or NULL */
+  const void* proj_weight;   /* [C,C] fp16 */
+  const float* proj_bias;    /* [C] or NULL */
+  const float* temperature;  /* [H] fp32 (XCA only) */
+  void* y;                   /* [B,N,C] */
+} pa_xcit_args;
+size_t pa_xca_workspace_bytes(const pa_xcit_args* a);
+int pa_xca_fwd(const pa_xcit_args* a, void* workspace, size_t workspace_bytes, void* stream);
+size_t pa_class_attn_workspace_bytes(const pa_xcit_args* a);
+int pa_class_attn_fwd(const pa_xcit_args* a, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- cswin.LePEAttention (cswin.py:51-127) */
+typedef struct {
+  int B, L, C, H;            /* C = channels of this branch, C / H in {32, 64}; L == resolution^2 */
+  int resolution, idx, split_size;   /* idx: -1 full window, 0 full-height stripes, 1 full-width stripes (cswin.py:62-67) */
+  float scale;
+  const void* q; const void* k; const void* v;   /* fp16, each [B, L, C] with row pitch ld and image pitch batch_stride */
+  long long ld, batch_stride;
+  const float* get_v_weight_t;   /* [9, C] fp32: get_v.weight [C,1,3,3] transposed */
+  const float* get_v_bias;       /* [C] */
+  void* out; long long ldo, out_batch_stride;    /* fp16 [B, L, C] */
+} pa_cswin_lepe_args;
+int pa_cswin_lepe_fwd(const pa_cswin_lepe_args* a, void* stream);
+
+/* ---------------------------------------------------------------- cswin.CSWinBlock attention half (cswin.py:176-194) */
+typedef struct {
+  int dtype, out_dtype;
+  int B, L, C, H;            /* H = num_heads of the block */
+  int reso, split_size, last_stage;
+  int residual;              /* 1: y = x + proj(...) (cswin.py:194); 0: y = proj(...) */
+  float scale, ln_eps;
+  const void* x;             /* [B,L,C] */
+  const float* norm1_weight; const float* norm1_bias;
+  const void* qkv_weight;    /* [3C,C] fp16 */
+  const float* qkv_bias;     /* [3C] or NULL */
+  const void* proj_weight;   /* [C,C] fp16 */
+  const float* proj_bias;
+  const float* get_v_weight_t[2];   /* per branch: [9, C/branches] fp32 */
+  const float* get_v_bias[2];
+  void* y;                   /* [B,L,C] */
+} pa_cswin_block_args;
+size_t pa_cswin_block_attn_workspace_bytes(const pa_cswin_block_args* a);
+int pa_cswin_block_attn_fwd(const pa_cswin_block_args* a, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

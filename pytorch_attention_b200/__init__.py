@@ -2,10 +2,17 @@
 changzy00/pytorch-attention's vision_transformers/ (ViT, PVT, CvT, CSWin, XCiT).
 
 Python here is plumbing only (module state, device memory, streams); all arithmetic runs in the hand-written
-CUDA library ``lib/libpa_b200.so`` behind the C ABI declared in ``include/pa_b200.h``.
+CUDA library ``lib/libpa_b200.so`` behind the C ABI declared in ``include/pa_b200.h``.  The sub-modules mirror
+the reference's file names so that ``from pytorch_attention_b200.pvt import Attention`` replaces
+``from pvt import Attention``.
 """
 from . import _lib, ops  # noqa: F401
-from . import vit  # noqa: F401
+from . import vit, pvt, cvt, cswin, xcit  # noqa: F401
 from .vit import Attention as ViTAttention  # noqa: F401
+from .pvt import Attention as PVTAttention  # noqa: F401
+from .cvt import Attention as CvTAttention  # noqa: F401
+from .cswin import LePEAttention, CSWinBlock  # noqa: F401
+from .xcit import XCA, ClassAttention  # noqa: F401
 
-__all__ = ["ops", "vit", "ViTAttention"]
+__all__ = ["ops", "vit", "pvt", "cvt", "cswin", "xcit", "ViTAttention", "PVTAttention", "CvTAttention",
+           "LePEAttention", "CSWinBlock", "XCA", "ClassAttention"]

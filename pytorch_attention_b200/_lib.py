@@ -21,7 +21,8 @@ class GemmArgs(C.Structure):
                 ("A", _vp), ("lda", _ll), ("a_batch", _ll),
                 ("B", _vp), ("ldb", _ll), ("b_batch", _ll),
                 ("D", _vp), ("ldd", _ll), ("d_batch", _ll),
-                ("bias", _vp), ("bias_mode", _i), ("block_n", _i)]
+                ("bias", _vp), ("bias_mode", _i), ("block_n", _i),
+                ("residual", _vp), ("ldr", _ll), ("r_batch", _ll), ("res_dtype", _i)]
 
 
 class AttnArgs(C.Structure):
@@ -29,13 +30,50 @@ class AttnArgs(C.Structure):
                 ("q", _vp), ("ldq", _ll), ("q_group", _ll), ("q_col0", _i),
                 ("kv", _vp), ("ldkv", _ll), ("kv_group", _ll), ("k_col0", _i), ("v_col0", _i),
                 ("o", _vp), ("ldo", _ll), ("o_group", _ll), ("o_col0", _i),
-                ("scale", _f)]
+                ("scale", _f), ("head_dim", _i)]
 
 
 class VitArgs(C.Structure):
     _fields_ = [("dtype", _i), ("out_dtype", _i), ("B", _i), ("N", _i), ("C", _i), ("H", _i),
                 ("scale", _f),
                 ("x", _vp), ("qkv_weight", _vp), ("qkv_bias", _vp), ("proj_weight", _vp), ("proj_bias", _vp),
+                ("y", _vp)]
+
+
+class PvtArgs(C.Structure):
+    _fields_ = [("dtype", _i), ("out_dtype", _i), ("B", _i), ("N", _i), ("C", _i), ("H", _i),
+                ("Himg", _i), ("Wimg", _i), ("sr", _i), ("scale", _f),
+                ("x", _vp), ("q_weight", _vp), ("q_bias", _vp), ("kv_weight", _vp), ("kv_bias", _vp),
+                ("proj_weight", _vp), ("proj_bias", _vp), ("sr_weight_t", _vp), ("sr_scale", _vp), ("sr_shift", _vp),
+                ("y", _vp)]
+
+
+class CvtArgs(C.Structure):
+    _fields_ = [("dtype", _i), ("out_dtype", _i), ("B", _i), ("C", _i), ("H", _i), ("Himg", _i), ("Wimg", _i), ("ks", _i),
+                ("scale", _f),
+                ("x", _vp), ("dw_weight", _vp), ("dw_scale", _vp), ("dw_shift", _vp), ("qkv_weight", _vp), ("qkv_bias", _vp),
+                ("proj_weight", _vp), ("proj_bias", _vp), ("y", _vp)]
+
+
+class XcitArgs(C.Structure):
+    _fields_ = [("dtype", _i), ("out_dtype", _i), ("B", _i), ("N", _i), ("C", _i), ("H", _i), ("scale", _f),
+                ("x", _vp), ("qkv_weight", _vp), ("qkv_bias", _vp), ("proj_weight", _vp), ("proj_bias", _vp),
+                ("temperature", _vp), ("y", _vp)]
+
+
+class LepeArgs(C.Structure):
+    _fields_ = [("B", _i), ("L", _i), ("C", _i), ("H", _i), ("resolution", _i), ("idx", _i), ("split_size", _i),
+                ("scale", _f),
+                ("q", _vp), ("k", _vp), ("v", _vp), ("ld", _ll), ("batch_stride", _ll),
+                ("get_v_weight_t", _vp), ("get_v_bias", _vp),
+                ("out", _vp), ("ldo", _ll), ("out_batch_stride", _ll)]
+
+
+class CswinBlockArgs(C.Structure):
+    _fields_ = [("dtype", _i), ("out_dtype", _i), ("B", _i), ("L", _i), ("C", _i), ("H", _i),
+                ("reso", _i), ("split_size", _i), ("last_stage", _i), ("residual", _i), ("scale", _f), ("ln_eps", _f),
+                ("x", _vp), ("norm1_weight", _vp), ("norm1_bias", _vp), ("qkv_weight", _vp), ("qkv_bias", _vp),
+                ("proj_weight", _vp), ("proj_bias", _vp), ("get_v_weight_t", _vp * 2), ("get_v_bias", _vp * 2),
                 ("y", _vp)]
 
 
@@ -50,6 +88,17 @@ SYMBOLS = {
     "pa_attn_core": (_i, [C.POINTER(AttnArgs), _vp]),
     "pa_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitArgs)]),
     "pa_vit_fwd": (_i, [C.POINTER(VitArgs), _vp, C.c_size_t, _vp]),
+    "pa_pvt_workspace_bytes": (C.c_size_t, [C.POINTER(PvtArgs)]),
+    "pa_pvt_fwd": (_i, [C.POINTER(PvtArgs), _vp, C.c_size_t, _vp]),
+    "pa_cvt_workspace_bytes": (C.c_size_t, [C.POINTER(CvtArgs)]),
+    "pa_cvt_fwd": (_i, [C.POINTER(CvtArgs), _vp, C.c_size_t, _vp]),
+    "pa_xca_workspace_bytes": (C.c_size_t, [C.POINTER(XcitArgs)]),
+    "pa_xca_fwd": (_i, [C.POINTER(XcitArgs), _vp, C.c_size_t, _vp]),
+    "pa_class_attn_workspace_bytes": (C.c_size_t, [C.POINTER(XcitArgs)]),
+    "pa_class_attn_fwd": (_i, [C.POINTER(XcitArgs), _vp, C.c_size_t, _vp]),
+    "pa_cswin_lepe_fwd": (_i, [C.POINTER(LepeArgs), _vp]),
+    "pa_cswin_block_attn_workspace_bytes": (C.c_size_t, [C.POINTER(CswinBlockArgs)]),
+    "pa_cswin_block_attn_fwd": (_i, [C.POINTER(CswinBlockArgs), _vp, C.c_size_t, _vp]),
 }
 
 _lock = threading.Lock()

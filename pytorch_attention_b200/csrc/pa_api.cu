@@ -2,15 +2,30 @@
 #include "pa_attn.cuh"
 #include "pa_gemm.cuh"
 #include "pa_host.cuh"
+#include "pa_misc.cuh"
 
 #include <math.h>
 #include <stdlib.h>
 
 using namespace pa;
 
-// ------------------------------------------------------------------------------------------------ GEMM
 namespace {
 
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// bump allocator over the caller's workspace
+struct Arena {
+  uint8_t* base;
+  size_t off;
+  explicit Arena(void* ws) : base(reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(ws), 1024))), off(0) {}
+  void* take(size_t bytes) {
+    void* p = base + off;
+    off += align_up(bytes, 1024);
+    return p;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ GEMM
 template <int BN, int ST>
 int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, ST>;
@@ -91,6 +106,7 @@ int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
   p.b_batched = a->b_batch != 0;
   p.D = a->D; p.ldd = a->ldd; p.d_batch = a->d_batch;
   p.bias = a->bias; p.bias_mode = a->bias_mode; p.out_dtype = a->out_dtype;
+  p.residual = a->residual; p.ldr = a->ldr; p.r_batch = a->r_batch; p.res_dtype = a->res_dtype;
   p.idesc = make_idesc(128, bn, a->a_dtype, a->b_dtype, 0, 0);
   switch (bn) {
     case 256: return launch_gemm_cfg<256, 4>(tmA, tmB, p, st);
@@ -102,61 +118,147 @@ int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
   }
 }
 
+// small helper for the plain 2-D "y = x W^T + b" uses
+int linear(const void* x, int x_dtype, long long ldx, const void* w, int w_dtype, const float* bias, void* y, int y_dtype,
+           long long ldy, long long M, int N, int K, cudaStream_t st, const void* residual = nullptr, long long ldr = 0,
+           int res_dtype = 0) {
+  pa_gemm_args g = {};
+  g.a_dtype = x_dtype; g.b_dtype = w_dtype; g.out_dtype = y_dtype;
+  g.M = (int)M; g.N = N; g.K = K; g.Z = 1;
+  g.A = x; g.lda = ldx; g.B = w; g.ldb = K; g.D = y; g.ldd = ldy;
+  g.bias = bias; g.bias_mode = bias ? 1 : 0;
+  g.residual = residual; g.ldr = ldr; g.res_dtype = res_dtype;
+  return gemm_impl(&g, st);
+}
+
 // ------------------------------------------------------------------------------------------------ attention core
-int attn_impl(const pa_attn_args* a, cudaStream_t st) {
-  if (!a) return fail(PA_ERR_NULL, "pa_attn_core: args is NULL");
-  if (!a->q || !a->kv || !a->o) return fail(PA_ERR_NULL, "pa_attn_core: q/kv/o must be non-NULL");
-  if (a->G <= 0 || a->H <= 0 || a->n_q <= 0 || a->n_k <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_attn_core: G,H,n_q,n_k must be positive");
-  if (a->n_k > 256) return fail(PA_ERR_UNSUPPORTED, "pa_attn_core: n_k=%d > 256 keys per unit not supported by this kernel", a->n_k);
-  if (!(a->scale > 0.f)) return fail(PA_ERR_UNSUPPORTED, "pa_attn_core: scale must be > 0");
-  if (a->ldo % 8 || a->o_col0 % 8 || a->o_group % 8 || (reinterpret_cast<uintptr_t>(a->o) & 15))
-    return fail(PA_ERR_MISALIGNED, "pa_attn_core: output pitch/offset must be multiples of 8 elements");
-  int rc = current_device_check();
-  if (rc) return rc;
+struct AttnLaunch {
+  int hd;                 // 64 or 32
+  bool windowed;
+  int G, H, n_q, n_k;     // non-windowed: G groups of n_q / n_k rows.  windowed: filled from the geometry below
+  const void *q, *k, *v;
+  long long ldq, q_group; // row pitch / group pitch of q (elements); windowed: ldq = token pitch, q_group = image pitch
+  long long ldk, k_group; // same for k and v (they share pitches)
+  int q_col0, k_col0, v_col0;
+  void* o; long long ldo, o_group; int o_col0;
+  float scale;
+  int B, R, H_sp, W_sp;   // windowed: images, resolution, window shape
+  int add_into_out;
+};
 
-  AttnParams p;
-  p.G = a->G; p.H = a->H; p.n_q = a->n_q; p.n_k = a->n_k;
-  p.kp = (a->n_k + 15) / 16 * 16;
-  p.q_tiles = (a->n_q + 127) / 128;
-  p.pairs = (p.q_tiles + 1) / 2;
-  p.items = a->G * a->H * p.pairs;
-  p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.v_col0 = a->v_col0;
-  p.O = a->o; p.ldo = a->ldo; p.o_group = a->o_group; p.o_col0 = a->o_col0;
-  p.scale_log2e = a->scale * 1.4426950408889634f;
-  p.idesc_s = make_idesc(128, p.kp, PA_F16, PA_F16, 0, 0);
-  p.idesc_o = make_idesc(128, ATTN_HD, PA_F16, PA_F16, 0, 1);
-
-  CUtensorMap tmQ, tmKV;
-  {
-    uint64_t dims[3] = {(uint64_t)a->ldq, (uint64_t)a->n_q, (uint64_t)a->G};
-    uint64_t str[2] = {(uint64_t)a->ldq * 2, (uint64_t)a->q_group * 2};
-    uint32_t box[3] = {ATTN_HD, 128, 1};
-    rc = make_tmap_16b(&tmQ, PA_DTYPE_F16, a->q, 3, dims, str, box);
-    if (rc) return rc;
-  }
-  {
-    uint64_t dims[3] = {(uint64_t)a->ldkv, (uint64_t)a->n_k, (uint64_t)a->G};
-    uint64_t str[2] = {(uint64_t)a->ldkv * 2, (uint64_t)a->kv_group * 2};
-    uint32_t box[3] = {ATTN_HD, (uint32_t)p.kp, 1};
-    rc = make_tmap_16b(&tmKV, PA_DTYPE_F16, a->kv, 3, dims, str, box);
-    if (rc) return rc;
-  }
-  const int smem = attn_smem_bytes(p.kp);
+template <int HD, bool WIN>
+int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int smem,
+                  cudaStream_t st) {
   static int attr_smem[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (attr_smem[dev & 63] < smem) {
-    PA_CUDA_OK(cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(256)));
-    attr_smem[dev & 63] = attn_smem_bytes(256);
+    PA_CUDA_OK(cudaFuncSetAttribute(attn_core_kernel<HD, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem[dev & 63] = smem;
   }
   const int grid = p.items < num_sms() ? p.items : num_sms();
-  attn_core_kernel<<<grid, ATTN_THREADS, smem, st>>>(tmQ, tmKV, p);
+  attn_core_kernel<HD, WIN><<<grid, ATTN_THREADS, smem, st>>>(tq, tk, tv, p);
   PA_CUDA_OK(cudaGetLastError());
   launch_counter()++;
   return PA_OK;
 }
 
-inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+int attn_launch(const AttnLaunch& a, cudaStream_t st) {
+  if (a.hd != 64 && a.hd != 32) return fail(PA_ERR_UNSUPPORTED, "attention core: head_dim %d unsupported (64 or 32)", a.hd);
+  if (!(a.scale > 0.f)) return fail(PA_ERR_UNSUPPORTED, "attention core: scale must be > 0");
+  if (a.ldo % 8 || a.o_col0 % 8 || a.o_group % 8 || (reinterpret_cast<uintptr_t>(a.o) & 15))
+    return fail(PA_ERR_MISALIGNED, "attention core: output pitch/offset must be multiples of 8 elements");
+  int rc = current_device_check();
+  if (rc) return rc;
+  const int hd = a.hd;
+  const int kb_max_multi = 256 - hd;
+  const TmapSwizzle swz = hd == 64 ? TM_SWZ_128 : TM_SWZ_64;
+
+  AttnParams p = {};
+  p.H = a.H;
+  p.q_col0 = a.q_col0; p.k_col0 = a.k_col0; p.v_col0 = a.v_col0;
+  p.O = a.o; p.ldo = a.ldo; p.o_group = a.o_group; p.o_col0 = a.o_col0;
+  p.scale_log2e = a.scale * 1.4426950408889634f;
+  p.add_into_out = a.add_into_out;
+  CUtensorMap tq, tk, tv;
+
+  if (!a.windowed) {
+    p.G = a.G; p.n_q = a.n_q; p.n_k = a.n_k;
+    if (a.n_k <= 256) { p.nkb = 1; p.kb = (a.n_k + 15) / 16 * 16; }
+    else { p.kb = kb_max_multi; p.nkb = (a.n_k + p.kb - 1) / p.kb; }
+    p.kb_rows = p.kb;
+    {
+      uint64_t dims[3] = {(uint64_t)a.ldq, (uint64_t)a.n_q, (uint64_t)a.G};
+      uint64_t str[2] = {(uint64_t)a.ldq * 2, (uint64_t)a.q_group * 2};
+      uint32_t box[3] = {(uint32_t)hd, 128, 1};
+      if ((rc = make_tmap_16b(&tq, PA_DTYPE_F16, a.q, 3, dims, str, box, swz))) return rc;
+    }
+    {
+      uint64_t dims[3] = {(uint64_t)a.ldk, (uint64_t)a.n_k, (uint64_t)a.G};
+      uint64_t str[2] = {(uint64_t)a.ldk * 2, (uint64_t)a.k_group * 2};
+      uint32_t box[3] = {(uint32_t)hd, (uint32_t)p.kb, 1};
+      if ((rc = make_tmap_16b(&tk, PA_DTYPE_F16, a.k, 3, dims, str, box, swz))) return rc;
+      if ((rc = make_tmap_16b(&tv, PA_DTYPE_F16, a.v, 3, dims, str, box, swz))) return rc;
+    }
+  } else {
+    const int R = a.R, Hs = a.H_sp, Ws = a.W_sp;
+    if (R % Hs || R % Ws) return fail(PA_ERR_BAD_SHAPE, "windowed attention: resolution %d not divisible by window %dx%d", R, Hs, Ws);
+    const int nI = R / Hs, nJ = R / Ws, Nw = Hs * Ws;
+    p.R = R; p.H_sp = Hs; p.W_sp = Ws; p.nJ = nJ; p.nWin = nI * nJ;
+    p.G = a.B * p.nWin; p.n_q = Nw; p.n_k = Nw;
+    if (Ws > 256) return fail(PA_ERR_UNSUPPORTED, "windowed attention: window width %d > 256", Ws);
+    if (Nw <= 256) { p.h_box = Hs; p.nkb = 1; p.kb_rows = Nw; p.kb = (Nw + 15) / 16 * 16; }
+    else {
+      int hb = kb_max_multi / Ws;
+      while (hb > 0 && (Ws * hb) % 8 != 0) --hb;       // block buffers must start on an 8-row swizzle atom
+      if (hb <= 0) return fail(PA_ERR_UNSUPPORTED, "windowed attention: cannot block a %dx%d window", Hs, Ws);
+      p.h_box = hb; p.kb_rows = Ws * hb; p.kb = (p.kb_rows + 15) / 16 * 16; p.nkb = (Hs + hb - 1) / hb;
+    }
+    if (p.nkb * p.kb_rows > 512) return fail(PA_ERR_UNSUPPORTED, "windowed attention: window of %d tokens too large", Nw);
+    // 5-D view of the token matrix: {channel, col in window, window col, row in image-window, image*window row}
+    auto mk = [&](CUtensorMap* t, const void* base, long long ld, long long img_pitch) -> int {
+      if (img_pitch != (long long)R * R * ld) return fail(PA_ERR_UNSUPPORTED, "windowed attention: image pitch must equal L * row pitch");
+      uint64_t dims[5] = {(uint64_t)ld, (uint64_t)Ws, (uint64_t)nJ, (uint64_t)Hs, (uint64_t)a.B * nI};
+      uint64_t str[4] = {(uint64_t)ld * 2, (uint64_t)Ws * ld * 2, (uint64_t)R * ld * 2, (uint64_t)Hs * R * ld * 2};
+      uint32_t box[5] = {(uint32_t)hd, (uint32_t)Ws, 1, (uint32_t)p.h_box, 1};
+      return make_tmap_16b(t, PA_DTYPE_F16, base, 5, dims, str, box, swz);
+    };
+    if ((rc = mk(&tq, a.q, a.ldq, a.q_group))) return rc;
+    if ((rc = mk(&tk, a.k, a.ldk, a.k_group))) return rc;
+    if ((rc = mk(&tv, a.v, a.ldk, a.k_group))) return rc;
+  }
+  if (p.nkb > 1 && p.kb > kb_max_multi) return fail(PA_ERR_UNSUPPORTED, "attention core: key block %d too wide", p.kb);
+  p.q_tiles = (p.n_q + 127) / 128;
+  p.pairs = (p.q_tiles + 1) / 2;
+  p.items = p.G * p.H * p.pairs;
+  p.idesc_s = make_idesc(128, p.kb, PA_F16, PA_F16, 0, 0);
+  p.idesc_o = make_idesc(128, hd, PA_F16, PA_F16, 0, 1);
+  const int smem = attn_smem_bytes(hd, a.windowed, p.nkb, p.kb, p.kb_rows);
+  if (smem > 227 * 1024) return fail(PA_ERR_UNSUPPORTED, "attention core: shared memory plan %d B too large", smem);
+  if (hd == 64) return a.windowed ? launch_attn_t<64, true>(tq, tk, tv, p, smem, st) : launch_attn_t<64, false>(tq, tk, tv, p, smem, st);
+  return a.windowed ? launch_attn_t<32, true>(tq, tk, tv, p, smem, st) : launch_attn_t<32, false>(tq, tk, tv, p, smem, st);
+}
+
+int attn_impl(const pa_attn_args* a, cudaStream_t st) {
+  if (!a) return fail(PA_ERR_NULL, "pa_attn_core: args is NULL");
+  if (!a->q || !a->kv || !a->o) return fail(PA_ERR_NULL, "pa_attn_core: q/kv/o must be non-NULL");
+  if (a->G <= 0 || a->H <= 0 || a->n_q <= 0 || a->n_k <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_attn_core: G,H,n_q,n_k must be positive");
+  AttnLaunch l = {};
+  l.hd = a->head_dim ? a->head_dim : 64;
+  l.windowed = false;
+  l.G = a->G; l.H = a->H; l.n_q = a->n_q; l.n_k = a->n_k;
+  l.q = a->q; l.ldq = a->ldq; l.q_group = a->q_group; l.q_col0 = a->q_col0;
+  l.k = a->kv; l.v = a->kv; l.ldk = a->ldkv; l.k_group = a->kv_group; l.k_col0 = a->k_col0; l.v_col0 = a->v_col0;
+  l.o = a->o; l.ldo = a->ldo; l.o_group = a->o_group; l.o_col0 = a->o_col0;
+  l.scale = a->scale;
+  return attn_launch(l, st);
+}
+
+int grid_for(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
 
 }  // namespace
 
@@ -180,13 +282,12 @@ int pa_device_check(int device) {
 int pa_gemm_tn(const pa_gemm_args* a, void* stream) { return gemm_impl(a, (cudaStream_t)stream); }
 int pa_attn_core(const pa_attn_args* a, void* stream) { return attn_impl(a, (cudaStream_t)stream); }
 
-// ---------------------------------------------------------------- ViT
+// ================================================================ ViT  (ViT.py:67-89)
 static int vit_check(const pa_vit_args* a) {
   if (!a) return fail(PA_ERR_NULL, "pa_vit: args is NULL");
   if (a->B <= 0 || a->N <= 0 || a->C <= 0 || a->H <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_vit: B,N,C,H must be positive");
   if (a->C % a->H != 0) return fail(PA_ERR_BAD_SHAPE, "pa_vit: dim %d not divisible by num_heads %d (ViT.py:70)", a->C, a->H);
   if (a->C / a->H != 64) return fail(PA_ERR_UNSUPPORTED, "pa_vit: head_dim %d unsupported (64 only)", a->C / a->H);
-  if (a->N > 256) return fail(PA_ERR_UNSUPPORTED, "pa_vit: N=%d tokens > 256 not supported yet", a->N);
   if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "pa_vit: dtype must be fp16/bf16");
   return PA_OK;
 }
@@ -206,36 +307,333 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
   cudaStream_t st = (cudaStream_t)stream;
   const long long rows = (long long)a->B * a->N;
   const int C = a->C;
-  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
-  void* qkv = ws;
-  void* obuf = ws + align_up((size_t)rows * 3 * C * 2, 1024);
-
+  Arena ws(workspace);
+  void* qkv = ws.take((size_t)rows * 3 * C * 2);
+  void* obuf = ws.take((size_t)rows * C * 2);
   // 1. qkv[B*N, 3C] = x Wqkv^T (+b)          (ViT.py:81)
-  pa_gemm_args g1 = {};
-  g1.a_dtype = a->dtype; g1.b_dtype = a->dtype; g1.out_dtype = PA_DTYPE_F16;
-  g1.M = (int)rows; g1.N = 3 * C; g1.K = C; g1.Z = 1;
-  g1.A = a->x; g1.lda = C; g1.B = a->qkv_weight; g1.ldb = C;
-  g1.D = qkv; g1.ldd = 3 * C;
-  g1.bias = a->qkv_bias; g1.bias_mode = a->qkv_bias ? 1 : 0;
-  rc = gemm_impl(&g1, st);
-  if (rc) return rc;
-  // 2. per (b,h): softmax(q k^T scale) v       (ViT.py:83-86), O written as [B*N, C] with column h*64+d
-  pa_attn_args at = {};
-  at.G = a->B; at.H = a->H; at.n_q = a->N; at.n_k = a->N;
+  if ((rc = linear(a->x, a->dtype, C, a->qkv_weight, a->dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
+  // 2. per (b,h): softmax(q k^T scale) v       (ViT.py:83-86), O as [B*N, C] with column h*64+d
+  AttnLaunch at = {};
+  at.hd = 64; at.G = a->B; at.H = a->H; at.n_q = a->N; at.n_k = a->N;
   at.q = qkv; at.ldq = 3 * C; at.q_group = (long long)a->N * 3 * C; at.q_col0 = 0;
-  at.kv = qkv; at.ldkv = 3 * C; at.kv_group = (long long)a->N * 3 * C; at.k_col0 = C; at.v_col0 = 2 * C;
+  at.k = qkv; at.v = qkv; at.ldk = 3 * C; at.k_group = (long long)a->N * 3 * C; at.k_col0 = C; at.v_col0 = 2 * C;
   at.o = obuf; at.ldo = C; at.o_group = (long long)a->N * C; at.o_col0 = 0;
   at.scale = a->scale;
-  rc = attn_impl(&at, st);
-  if (rc) return rc;
+  if ((rc = attn_launch(at, st))) return rc;
   // 3. y = O Wproj^T + b                       (ViT.py:87)
-  pa_gemm_args g2 = {};
-  g2.a_dtype = PA_DTYPE_F16; g2.b_dtype = PA_DTYPE_F16; g2.out_dtype = a->out_dtype;
-  g2.M = (int)rows; g2.N = C; g2.K = C; g2.Z = 1;
-  g2.A = obuf; g2.lda = C; g2.B = a->proj_weight; g2.ldb = C;
-  g2.D = a->y; g2.ldd = C;
-  g2.bias = a->proj_bias; g2.bias_mode = a->proj_bias ? 1 : 0;
-  return gemm_impl(&g2, st);
+  return linear(obuf, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st);
+}
+
+// ================================================================ PVT  (pvt.py:52-91)
+static int pvt_check(const pa_pvt_args* a) {
+  if (!a) return fail(PA_ERR_NULL, "pa_pvt: args is NULL");
+  if (a->B <= 0 || a->C <= 0 || a->H <= 0 || a->Himg <= 0 || a->Wimg <= 0 || a->sr <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: sizes must be positive");
+  if (a->C % a->H != 0) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: dim %d not divisible by num_heads %d (pvt.py:56)", a->C, a->H);
+  if (a->C / a->H != 64) return fail(PA_ERR_UNSUPPORTED, "pa_pvt: head_dim %d unsupported (64 only)", a->C / a->H);
+  if (a->N != a->Himg * a->Wimg) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: N=%d != H*W=%d*%d", a->N, a->Himg, a->Wimg);
+  if (a->C % 8) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: dim must be a multiple of 8");
+  if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "pa_pvt: dtype must be fp16/bf16");
+  return PA_OK;
+}
+static inline int pvt_m(const pa_pvt_args* a) { return a->sr > 1 ? (a->Himg / a->sr) * (a->Wimg / a->sr) : a->N; }
+
+size_t pa_pvt_workspace_bytes(const pa_pvt_args* a) {
+  if (pvt_check(a)) return 0;
+  const size_t rows = (size_t)a->B * a->N, mrows = (size_t)a->B * pvt_m(a);
+  return align_up(mrows * a->C * 2, 1024) + align_up(rows * a->C * 2, 1024) * 2 + align_up(mrows * 2 * a->C * 2, 1024) + 1024;
+}
+
+int pa_pvt_fwd(const pa_pvt_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = pvt_check(a);
+  if (rc) return rc;
+  if (!a->x || !a->q_weight || !a->kv_weight || !a->proj_weight || !a->y) return fail(PA_ERR_NULL, "pa_pvt_fwd: x/weights/y must be non-NULL");
+  if (a->sr > 1 && (!a->sr_weight_t || !a->sr_scale || !a->sr_shift)) return fail(PA_ERR_NULL, "pa_pvt_fwd: sr_ratio>1 needs sr_weight_t/sr_scale/sr_shift");
+  const size_t need = pa_pvt_workspace_bytes(a);
+  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_pvt_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+  if ((rc = current_device_check())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = a->C, M = pvt_m(a);
+  const long long rows = (long long)a->B * a->N, mrows = (long long)a->B * M;
+  Arena ws(workspace);
+  void* xr = ws.take((size_t)mrows * C * 2);
+  void* qb = ws.take((size_t)rows * C * 2);
+  void* ob = ws.take((size_t)rows * C * 2);
+  void* kv = ws.take((size_t)mrows * 2 * C * 2);
+  const void* kv_in = a->x;
+  int kv_dtype = a->dtype;
+  if (a->sr > 1) {
+    // spatial reduction: depthwise conv (k = stride = sr) + eval BatchNorm folded into scale/shift   (pvt.py:77-78)
+    SrParams sp;
+    sp.x = a->x; sp.out = xr; sp.w = a->sr_weight_t; sp.scale = a->sr_scale; sp.shift = a->sr_shift;
+    sp.B = a->B; sp.H = a->Himg; sp.W = a->Wimg; sp.C = C; sp.sr = a->sr; sp.Hs = a->Himg / a->sr; sp.Ws = a->Wimg / a->sr;
+    sp.dtype = a->dtype;
+    sr_conv_bn_kernel<<<grid_for(mrows * (C / 8), 256), 256, 0, st>>>(sp);
+    PA_CUDA_OK(cudaGetLastError());
+    launch_counter()++;
+    kv_in = xr;
+    kv_dtype = PA_DTYPE_F16;
+  }
+  // q = x Wq^T (+b)  (pvt.py:75);  [k|v] = x_ [Wk;Wv]^T (+b)  (pvt.py:79-80 / 82-83)
+  if ((rc = linear(a->x, a->dtype, C, a->q_weight, a->dtype, a->q_bias, qb, PA_DTYPE_F16, C, rows, C, C, st))) return rc;
+  if ((rc = linear(kv_in, kv_dtype, C, a->kv_weight, kv_dtype, a->kv_bias, kv, PA_DTYPE_F16, 2 * C, mrows, 2 * C, C, st))) return rc;
+  AttnLaunch at = {};
+  at.hd = 64; at.G = a->B; at.H = a->H; at.n_q = a->N; at.n_k = M;
+  at.q = qb; at.ldq = C; at.q_group = (long long)a->N * C; at.q_col0 = 0;
+  at.k = kv; at.v = kv; at.ldk = 2 * C; at.k_group = (long long)M * 2 * C; at.k_col0 = 0; at.v_col0 = C;
+  at.o = ob; at.ldo = C; at.o_group = (long long)a->N * C; at.o_col0 = 0;
+  at.scale = a->scale;
+  if ((rc = attn_launch(at, st))) return rc;
+  return linear(ob, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st);
+}
+
+// ================================================================ CvT  (cvt.py:48-76)
+static int cvt_check(const pa_cvt_args* a) {
+  if (!a) return fail(PA_ERR_NULL, "pa_cvt: args is NULL");
+  if (a->B <= 0 || a->C <= 0 || a->H <= 0 || a->Himg <= 0 || a->Wimg <= 0 || a->ks <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_cvt: sizes must be positive");
+  if (a->C % a->H != 0) return fail(PA_ERR_BAD_SHAPE, "pa_cvt: dim %d not divisible by num_heads %d (cvt.py:51)", a->C, a->H);
+  if (a->C / a->H != 64) return fail(PA_ERR_UNSUPPORTED, "pa_cvt: head_dim %d unsupported (64 only)", a->C / a->H);
+  if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "pa_cvt: dtype must be fp16/bf16");
+  return PA_OK;
+}
+
+size_t pa_cvt_workspace_bytes(const pa_cvt_args* a) {
+  if (cvt_check(a)) return 0;
+  const size_t rows = (size_t)a->B * a->Himg * a->Wimg;
+  return align_up(rows * a->C * 2, 1024) * 2 + align_up(rows * 3 * a->C * 2, 1024) + 1024;
+}
+
+int pa_cvt_fwd(const pa_cvt_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = cvt_check(a);
+  if (rc) return rc;
+  if (!a->x || !a->dw_weight || !a->dw_scale || !a->dw_shift || !a->qkv_weight || !a->proj_weight || !a->y)
+    return fail(PA_ERR_NULL, "pa_cvt_fwd: x/weights/y must be non-NULL");
+  const size_t need = pa_cvt_workspace_bytes(a);
+  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_cvt_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+  if ((rc = current_device_check())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = a->C, HW = a->Himg * a->Wimg;
+  const long long rows = (long long)a->B * HW;
+  Arena ws(workspace);
+  void* tok = ws.take((size_t)rows * C * 2);
+  void* ob = ws.take((size_t)rows * C * 2);
+  void* qkv = ws.take((size_t)rows * 3 * C * 2);
+  // depthwise conv + eval BN, NCHW -> token-major   (cvt.py:55-57)
+  DwParams dp;
+  dp.x = a->x; dp.out = tok; dp.w = a->dw_weight; dp.scale = a->dw_scale; dp.shift = a->dw_shift;
+  dp.B = a->B; dp.C = C; dp.H = a->Himg; dp.W = a->Wimg; dp.ks = a->ks; dp.dtype = a->dtype;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, a->B);
+  dwconv_bn_to_tokens_kernel<<<grid, 256, 0, st>>>(dp);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  // 1x1 conv == linear over channels   (cvt.py:58), rows ordered (s,h,d) as ViT (cvt.py:66)
+  if ((rc = linear(tok, PA_DTYPE_F16, C, a->qkv_weight, PA_DTYPE_F16, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
+  AttnLaunch at = {};
+  at.hd = 64; at.G = a->B; at.H = a->H; at.n_q = HW; at.n_k = HW;
+  at.q = qkv; at.ldq = 3 * C; at.q_group = (long long)HW * 3 * C; at.q_col0 = 0;
+  at.k = qkv; at.v = qkv; at.ldk = 3 * C; at.k_group = (long long)HW * 3 * C; at.k_col0 = C; at.v_col0 = 2 * C;
+  at.o = ob; at.ldo = C; at.o_group = (long long)HW * C; at.o_col0 = 0;
+  at.scale = a->scale;
+  if ((rc = attn_launch(at, st))) return rc;
+  // proj 1x1 conv straight into NCHW: y[b] [C, HW] = Wp [C, C] . O[b]^T  + bias per row   (cvt.py:74)
+  pa_gemm_args g = {};
+  g.a_dtype = PA_DTYPE_F16; g.b_dtype = PA_DTYPE_F16; g.out_dtype = a->out_dtype;
+  g.M = C; g.N = HW; g.K = C; g.Z = a->B;
+  g.A = a->proj_weight; g.lda = C; g.a_batch = 0;
+  g.B = ob; g.ldb = C; g.b_batch = (long long)HW * C;
+  g.D = a->y; g.ldd = HW; g.d_batch = (long long)C * HW;
+  g.bias = a->proj_bias; g.bias_mode = a->proj_bias ? 2 : 0;
+  return gemm_impl(&g, st);
+}
+
+// ================================================================ XCiT  (xcit.py:233-265, 159-188)
+static int xc_check(const pa_xcit_args* a, const char* who) {
+  if (!a) return fail(PA_ERR_NULL, "%s: args is NULL", who);
+  if (a->B <= 0 || a->N <= 0 || a->C <= 0 || a->H <= 0) return fail(PA_ERR_BAD_SHAPE, "%s: B,N,C,H must be positive", who);
+  if (a->C % a->H != 0) return fail(PA_ERR_BAD_SHAPE, "%s: dim %d not divisible by num_heads %d", who, a->C, a->H);
+  if (a->C / a->H != 64) return fail(PA_ERR_UNSUPPORTED, "%s: head_dim %d unsupported (64 only)", who, a->C / a->H);
+  if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "%s: dtype must be fp16/bf16", who);
+  return PA_OK;
+}
+
+size_t pa_xca_workspace_bytes(const pa_xcit_args* a) {
+  if (xc_check(a, "pa_xca")) return 0;
+  const size_t rows = (size_t)a->B * a->N;
+  return align_up(rows * 3 * a->C * 2, 1024) + align_up(rows * a->C * 2, 1024) + 1024;
+}
+
+int pa_xca_fwd(const pa_xcit_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = xc_check(a, "pa_xca");
+  if (rc) return rc;
+  if (!a->x || !a->qkv_weight || !a->proj_weight || !a->temperature || !a->y) return fail(PA_ERR_NULL, "pa_xca_fwd: x/weights/temperature/y must be non-NULL");
+  const size_t need = pa_xca_workspace_bytes(a);
+  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_xca_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+  if ((rc = current_device_check())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = a->C;
+  const long long rows = (long long)a->B * a->N;
+  Arena ws(workspace);
+  void* qkv = ws.take((size_t)rows * 3 * C * 2);
+  void* ob = ws.take((size_t)rows * C * 2);
+  if ((rc = linear(a->x, a->dtype, C, a->qkv_weight, a->dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
+  XcaParams xp;
+  xp.qkv = qkv; xp.out = ob; xp.temperature = a->temperature; xp.B = a->B; xp.N = a->N; xp.C = C; xp.H = a->H;
+  xca_core_kernel<<<a->B * a->H, 256, 0, st>>>(xp);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  return linear(ob, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st);
+}
+
+size_t pa_class_attn_workspace_bytes(const pa_xcit_args* a) {
+  if (xc_check(a, "pa_class_attn")) return 0;
+  const size_t rows = (size_t)a->B * a->N;
+  return align_up(rows * 3 * a->C * 2, 1024) + align_up((size_t)a->B * a->C * 2, 1024) + 1024;
+}
+
+int pa_class_attn_fwd(const pa_xcit_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = xc_check(a, "pa_class_attn");
+  if (rc) return rc;
+  if (!a->x || !a->qkv_weight || !a->proj_weight || !a->y) return fail(PA_ERR_NULL, "pa_class_attn_fwd: x/weights/y must be non-NULL");
+  if (a->out_dtype != a->dtype) return fail(PA_ERR_UNSUPPORTED, "pa_class_attn_fwd: y must have the dtype of x (patch tokens pass through unchanged, xcit.py:187)");
+  const size_t need = pa_class_attn_workspace_bytes(a);
+  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_class_attn_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+  if ((rc = current_device_check())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = a->C;
+  const long long rows = (long long)a->B * a->N;
+  if (((long long)rows * C * 2) % 16) return fail(PA_ERR_MISALIGNED, "pa_class_attn_fwd: B*N*C must be a multiple of 8");
+  Arena ws(workspace);
+  void* qkv = ws.take((size_t)rows * 3 * C * 2);
+  void* cls = ws.take((size_t)a->B * C * 2);
+  if ((rc = linear(a->x, a->dtype, C, a->qkv_weight, a->dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
+  ClsParams cp;
+  cp.qkv = qkv; cp.out = cls; cp.B = a->B; cp.N = a->N; cp.C = C; cp.H = a->H; cp.scale = a->scale;
+  class_attn_core_kernel<<<a->B * a->H, 256, a->N * sizeof(float), st>>>(cp);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  // y = x (patch tokens pass through, xcit.py:187), then row 0 of every image <- proj(cls)  (xcit.py:186)
+  const long long n16 = rows * C * 2 / 16;
+  copy16_kernel<<<grid_for(n16, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(a->x), reinterpret_cast<uint4*>(a->y), n16);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  return linear(cls, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, (long long)a->N * C, a->B, C, C, st);
+}
+
+// ================================================================ CSWin  (cswin.py:51-127, 130-197)
+static int lepe_geom(int resolution, int idx, int split, int* Hs, int* Ws) {
+  if (idx == -1) { *Hs = resolution; *Ws = resolution; }
+  else if (idx == 0) { *Hs = resolution; *Ws = split; }
+  else if (idx == 1) { *Hs = split; *Ws = resolution; }
+  else return fail(PA_ERR_UNSUPPORTED, "ERROR MODE %d (cswin.py:68-70: idx must be -1, 0 or 1)", idx);
+  return PA_OK;
+}
+
+static int lepe_check(const pa_cswin_lepe_args* a) {
+  if (!a) return fail(PA_ERR_NULL, "pa_cswin_lepe: args is NULL");
+  if (a->B <= 0 || a->L <= 0 || a->C <= 0 || a->H <= 0 || a->resolution <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_cswin_lepe: sizes must be positive");
+  if (a->L != a->resolution * a->resolution) return fail(PA_ERR_BAD_SHAPE, "flatten img_tokens has wrong size (cswin.py:110): L=%d, resolution=%d", a->L, a->resolution);
+  if (a->C % a->H != 0) return fail(PA_ERR_BAD_SHAPE, "pa_cswin_lepe: dim %d not divisible by num_heads %d", a->C, a->H);
+  if (a->C / a->H != 32 && a->C / a->H != 64) return fail(PA_ERR_UNSUPPORTED, "pa_cswin_lepe: head_dim %d unsupported (32 or 64)", a->C / a->H);
+  int Hs, Ws;
+  return lepe_geom(a->resolution, a->idx, a->split_size, &Hs, &Ws);
+}
+
+static int lepe_run(const pa_cswin_lepe_args* a, cudaStream_t st) {
+  int Hs = 0, Ws = 0, rc;
+  if ((rc = lepe_geom(a->resolution, a->idx, a->split_size, &Hs, &Ws))) return rc;
+  if (a->resolution % Hs || a->resolution % Ws) return fail(PA_ERR_BAD_SHAPE, "pa_cswin_lepe: resolution %d not divisible by window %dx%d", a->resolution, Hs, Ws);
+  if (a->C % 8 || a->ld % 8 || a->ldo % 8) return fail(PA_ERR_MISALIGNED, "pa_cswin_lepe: channel counts / pitches must be multiples of 8");
+  if ((rc = current_device_check())) return rc;
+  // LePE first: out = dwconv3x3(v) per window (cswin.py:93-96) ...
+  LepeParams lp;
+  lp.v = a->v; lp.out = a->out; lp.w = a->get_v_weight_t; lp.bias = a->get_v_bias;
+  lp.ldv = a->ld; lp.ldo = a->ldo; lp.v_col0 = 0; lp.o_col0 = 0;
+  lp.B = a->B; lp.R = a->resolution; lp.Cb = a->C; lp.H_sp = Hs; lp.W_sp = Ws;
+  if (a->batch_stride != (long long)a->L * a->ld || a->out_batch_stride != (long long)a->L * a->ldo)
+    return fail(PA_ERR_UNSUPPORTED, "pa_cswin_lepe: batch pitch must equal L * row pitch");
+  lepe_kernel<<<grid_for((long long)a->B * a->L * (a->C / 8), 256), 256, 0, st>>>(lp);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  // ... then the windowed attention adds softmax(q k^T scale) v on top (cswin.py:116-121) and scatters to image order (122-125)
+  AttnLaunch at = {};
+  at.hd = a->C / a->H; at.windowed = true; at.H = a->H;
+  at.q = a->q; at.k = a->k; at.v = a->v;
+  at.ldq = a->ld; at.q_group = a->batch_stride; at.ldk = a->ld; at.k_group = a->batch_stride;
+  at.q_col0 = 0; at.k_col0 = 0; at.v_col0 = 0;
+  at.o = a->out; at.ldo = a->ldo; at.o_group = a->out_batch_stride; at.o_col0 = 0;
+  at.scale = a->scale;
+  at.B = a->B; at.R = a->resolution; at.H_sp = Hs; at.W_sp = Ws;
+  at.add_into_out = 1;
+  return attn_launch(at, st);
+}
+
+int pa_cswin_lepe_fwd(const pa_cswin_lepe_args* a, void* stream) {
+  int rc = lepe_check(a);
+  if (rc) return rc;
+  if (!a->q || !a->k || !a->v || !a->get_v_weight_t || !a->get_v_bias || !a->out) return fail(PA_ERR_NULL, "pa_cswin_lepe_fwd: q/k/v/get_v/out must be non-NULL");
+  return lepe_run(a, (cudaStream_t)stream);
+}
+
+static int blk_check(const pa_cswin_block_args* a) {
+  if (!a) return fail(PA_ERR_NULL, "pa_cswin_block: args is NULL");
+  if (a->B <= 0 || a->C <= 0 || a->H <= 0 || a->reso <= 0 || a->split_size <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_cswin_block: sizes must be positive");
+  if (a->L != a->reso * a->reso) return fail(PA_ERR_BAD_SHAPE, "flatten img_tokens has wrong size (cswin.py:183): L=%d, reso=%d", a->L, a->reso);
+  const int branches = a->last_stage ? 1 : 2;
+  if (a->H % branches || a->C % (2 * branches)) return fail(PA_ERR_BAD_SHAPE, "pa_cswin_block: dim/heads not divisible by the branch count");
+  const int hd = (a->C / branches) / (a->H / branches);
+  if (hd != 32 && hd != 64) return fail(PA_ERR_UNSUPPORTED, "pa_cswin_block: head_dim %d unsupported (32 or 64)", hd);
+  if (a->C % 8) return fail(PA_ERR_BAD_SHAPE, "pa_cswin_block: dim must be a multiple of 8");
+  if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "pa_cswin_block: dtype must be fp16/bf16");
+  return PA_OK;
+}
+
+size_t pa_cswin_block_attn_workspace_bytes(const pa_cswin_block_args* a) {
+  if (blk_check(a)) return 0;
+  const size_t rows = (size_t)a->B * a->L;
+  return align_up(rows * a->C * 2, 1024) * 2 + align_up(rows * 3 * a->C * 2, 1024) + 1024;
+}
+
+int pa_cswin_block_attn_fwd(const pa_cswin_block_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = blk_check(a);
+  if (rc) return rc;
+  if (!a->x || !a->norm1_weight || !a->norm1_bias || !a->qkv_weight || !a->proj_weight || !a->get_v_weight_t[0] || !a->get_v_bias[0] || !a->y)
+    return fail(PA_ERR_NULL, "pa_cswin_block_attn_fwd: x/norm1/qkv/proj/get_v/y must be non-NULL");
+  const int branches = a->last_stage ? 1 : 2;
+  if (branches == 2 && (!a->get_v_weight_t[1] || !a->get_v_bias[1])) return fail(PA_ERR_NULL, "pa_cswin_block_attn_fwd: second branch get_v missing");
+  const size_t need = pa_cswin_block_attn_workspace_bytes(a);
+  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_cswin_block_attn_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+  if ((rc = current_device_check())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = a->C;
+  const long long rows = (long long)a->B * a->L;
+  Arena ws(workspace);
+  void* img = ws.take((size_t)rows * C * 2);
+  void* att = ws.take((size_t)rows * C * 2);
+  void* qkv = ws.take((size_t)rows * 3 * C * 2);
+  // img = norm1(x)   (cswin.py:184)
+  LnParams ln;
+  ln.x = a->x; ln.out = img; ln.gamma = a->norm1_weight; ln.beta = a->norm1_bias; ln.rows = rows; ln.C = C; ln.dtype = a->dtype; ln.eps = a->ln_eps;
+  layernorm_kernel<<<(int)((rows * 32 + 255) / 256), 256, 0, st>>>(ln);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  // qkv = Linear(C, 3C)(img), column o -> (s, c) = (o / C, o % C)   (cswin.py:185)
+  if ((rc = linear(img, PA_DTYPE_F16, C, a->qkv_weight, PA_DTYPE_F16, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
+  // branches on channel halves (cswin.py:187-192); each writes its half of `att` (the torch.cat of :190)
+  const int Cb = C / branches;
+  for (int br = 0; br < branches; ++br) {
+    pa_cswin_lepe_args l = {};
+    l.B = a->B; l.L = a->L; l.C = Cb; l.H = a->H / branches;
+    l.resolution = a->reso; l.idx = a->last_stage ? -1 : br; l.split_size = a->split_size;
+    l.scale = a->scale;
+    const uint16_t* base = reinterpret_cast<const uint16_t*>(qkv) + br * Cb;
+    l.q = base; l.k = base + C; l.v = base + 2 * C;
+    l.ld = 3 * C; l.batch_stride = (long long)a->L * 3 * C;
+    l.get_v_weight_t = a->get_v_weight_t[br]; l.get_v_bias = a->get_v_bias[br];
+    l.out = reinterpret_cast<uint16_t*>(att) + br * Cb; l.ldo = C; l.out_batch_stride = (long long)a->L * C;
+    if ((rc = lepe_run(&l, st))) return rc;
+  }
+  // y = x + proj(att)   (cswin.py:193-194)
+  return linear(att, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st,
+                a->residual ? a->x : nullptr, C, a->dtype);
 }
 
 }  // extern "C"

@@ -1,71 +1,112 @@
-// pa_attn.cuh — softmax(Q K^T * scale) V core on tcgen05 + TMEM, head_dim 64, keys per unit <= 256.
+// pa_attn.cuh — softmax(Q K^T * scale) V core on tcgen05 + TMEM.
 //
-// Work item = (group g, head h, pair of 128-row query tiles).  All keys of the unit fit one S tile, so the
-// row softmax is exact and single pass (no online rescaling).  Persistent CTA, 384 threads:
-//   warp 0     TMA producer: Q tile(s), K, V of the next item into a 2-deep smem ring (128B swizzle)
-//   warp 1     MMA issuer:   S_s = Q_s K^T  (SS, K-major both)  ->  TMEM slot s;   O_s = P_s V  (A = P from TMEM,
-//                            B = V MN-major straight from its natural [key][d] layout)
-//   warp 2     TMEM allocator (512 columns = 2 slots x 256)
-//   warps 4-7  softmax / epilogue warpgroup of slot 0   (thread <-> query row, TMEM lane)
-//   warps 8-11 softmax / epilogue warpgroup of slot 1
-// TMEM slot layout (columns): S fp32 [0, kp)   P fp16x2 [0, kp/2) (written in place behind the S reads)
-//                             O fp32 [192, 256) (written by the PV MMAs only after the softmax has drained S)
+// One templated persistent kernel serves every variant:
+//   HD        head dim 64 (ViT / PVT / CvT; 128B-swizzled rows) or 32 (CSWin; 64B-swizzled rows)
+//   WINDOWED  false: a unit's rows are consecutive tokens of a group (3-D TMA {cols, rows, group});
+//             true : a unit is one cross-shaped window of a CSWin image; rows are gathered straight from the
+//                    [B, H*W, ld] token matrix by a 5-D TMA box over {chan, col-in-window, window-col, row, image*window-row}
+//                    (box {HD, W_sp, 1, h_box, 1}; no img2windows copy),
+//                    and the epilogue scatters back to image order, adding onto the LePE term already there.
+// Work item = (group/window, head, pair of 128-row query tiles).  Keys are processed in blocks of <= 256-HD
+// (a single block may be up to 256 wide): one block -> exact single-pass softmax; several blocks -> online
+// softmax with the running O rescaled in TMEM (cheap: HD columns per row).
+//
+// 384 threads:  warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM allocator |
+//               warps 4-7 softmax+epilogue of slot 0 | warps 8-11 of slot 1   (thread <-> query row <-> TMEM lane)
+// TMEM slot (256 columns): S fp32 [0,kb)  ->  P fp16x2 [0,kb/2) written in place behind the S reads;
+//                          O fp32 [256-HD, 256) (aliases the tail of S only in the single-block case, where the
+//                          PV MMAs start after the softmax has drained S).
 #pragma once
 #include "pa_ptx.cuh"
 
 namespace pa {
 
 struct AttnParams {
-  int G, H;             // groups (batch entries), heads
-  int n_q, n_k;         // query / key rows per group
-  int kp;               // keys padded to a multiple of 16 (<= 256) = S tile width = K/V box rows
-  int q_tiles;          // ceil(n_q / 128)
-  int pairs;            // ceil(q_tiles / 2)
-  int items;            // G * H * pairs
+  int G, H;             // groups (batch entries or windows), heads
+  int n_q, n_k;         // query / key rows per unit
+  int kb;               // S tile width = key rows per block buffer, multiple of 16
+  int kb_rows;          // rows a K/V TMA box delivers per block (== kb unless windowed)
+  int nkb;              // key blocks per unit
+  int q_tiles, pairs, items;
   int q_col0, k_col0, v_col0;   // element column of head 0 inside the Q / KV tensor maps
-  void* O;              // fp16 output [G][n_q][ldo]
+  void* O;              // fp16 output
   long long ldo, o_group;
   int o_col0;
   float scale_log2e;    // softmax scale * log2(e)
   uint32_t idesc_s, idesc_o;
+  // windowed geometry (CSWin): image R x R, windows H_sp x W_sp, nJ windows per image row, nWin per image
+  int R, H_sp, W_sp, nJ, nWin, h_box;
+  int add_into_out;     // epilogue adds onto what O already holds (LePE)
 };
 
 constexpr int ATTN_THREADS = 384;
-constexpr int ATTN_HD = 64;
 constexpr int ATTN_SLOT_COLS = 256;
-constexpr int ATTN_O_COL = 192;
-constexpr int ATTN_Q_BYTES = 128 * ATTN_HD * 2;   // 16 KB per query tile
 
-__host__ __device__ inline int attn_item_bytes(int kp) { return 2 * ATTN_Q_BYTES + 2 * kp * ATTN_HD * 2; }
-__host__ __device__ inline int attn_smem_bytes(int kp) { return 2 * attn_item_bytes(kp) + 256 + 1024; }
+template <int HD>
+struct AttnCfg {
+  static constexpr int ROW_BYTES = HD * 2;                       // 128 (SW128) or 64 (SW64)
+  static constexpr int SBO = 8 * ROW_BYTES;                      // 8-row swizzle atom
+  static constexpr uint64_t SWZ = (HD == 64) ? PA_SWZ_128B : PA_SWZ_64B;
+  static constexpr int Q_TILE_BYTES = 128 * ROW_BYTES;
+  static constexpr int O_COL = ATTN_SLOT_COLS - HD;
+  static constexpr int V_KSTEP = 16 * ROW_BYTES / 16;            // descriptor advance (16 B units) per 16 keys
+};
 
+// Shared memory plan (host and device agree through these helpers)
+__host__ __device__ inline int attn_q_rows(bool windowed, int nkb, int kb_rows) {
+  const int r = windowed ? nkb * kb_rows : 256;
+  return ((r < 512 ? 512 : r) + 7) / 8 * 8;      // windowed: last query tile may start at row 384 -> keep 512 rows mapped
+}
+__host__ __device__ inline int attn_smem_bytes(int hd, bool windowed, int nkb, int kb, int kb_rows) {
+  const int q_rows = windowed ? attn_q_rows(true, nkb, kb_rows) : 256;
+  return 2 * q_rows * hd * 2 + 2 * 2 * kb * hd * 2 + 256 + 1024;
+}
+
+template <int HD, bool WINDOWED>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
-attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV,
                  const AttnParams p) {
+  using Cfg = AttnCfg<HD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int item_bytes = attn_item_bytes(p.kp);
-  const int kv_bytes = p.kp * ATTN_HD * 2;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * item_bytes);
-  uint64_t* item_full = bars;         // [2]  TMA -> MMA
-  uint64_t* item_empty = bars + 2;    // [2]  MMA -> TMA
-  uint64_t* s_full = bars + 4;        // [2]  MMA -> softmax(slot)
-  uint64_t* p_full = bars + 6;        // [2]  softmax(slot) -> MMA
-  uint64_t* o_full = bars + 8;        // [2]  MMA -> epilogue(slot)
-  uint64_t* slot_empty = bars + 10;   // [2]  epilogue(slot) -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const int q_rows = WINDOWED ? attn_q_rows(true, p.nkb, p.kb_rows) : 256;
+  const int q_bytes = q_rows * Cfg::ROW_BYTES;          // one Q buffer
+  const int kvb_bytes = p.kb * Cfg::ROW_BYTES;          // one K (or V) block buffer
+  uint8_t* q_smem = smem;                               // [2][q_bytes]
+  uint8_t* kv_smem = smem + 2 * q_bytes;                // [2 stages][K | V]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + 4 * kvb_bytes);
+  uint64_t* q_full = bars;            // [2] TMA -> MMA
+  uint64_t* q_empty = bars + 2;       // [2] MMA -> TMA
+  uint64_t* kv_full = bars + 4;       // [2]
+  uint64_t* kv_empty = bars + 6;      // [2]
+  uint64_t* s_full = bars + 8;        // [2] MMA -> softmax(slot): S block ready
+  uint64_t* p_full = bars + 10;       // [2] softmax(slot) -> MMA: P written (and O rescaled)
+  uint64_t* o_full = bars + 12;       // [2] MMA -> softmax(slot): PV of the block retired
+  uint64_t* slot_empty = bars + 14;   // [2] epilogue(slot) -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  if (WINDOWED) {
+    // rows never touched by TMA (tile padding beyond the window) must read as finite zeros
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = (2 * q_bytes + 4 * kvb_bytes) / 16;
+    for (int i = threadIdx.x; i < n16; i += ATTN_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&item_full[i], 1);
-      mbar_init(&item_empty[i], 1);
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
@@ -85,61 +126,96 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int b = 0;
-      uint32_t ph = 0;
+      int qb = 0, st = 0;
+      uint32_t qph = 0, kph = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int pr = item % p.pairs;
         const int gh = item / p.pairs;
         const int h = gh % p.H, g = gh / p.H;
-        const bool two = (2 * pr + 1) < p.q_tiles;
-        uint8_t* buf = smem + b * item_bytes;
-        mbar_wait(&item_empty[b], ph ^ 1);
-        mbar_expect_tx(&item_full[b], (two ? 2 : 1) * ATTN_Q_BYTES + 2 * kv_bytes);
-        tma_load_3d(buf, &tmQ, p.q_col0 + h * ATTN_HD, (2 * pr) * 128, g, &item_full[b]);
-        if (two) tma_load_3d(buf + ATTN_Q_BYTES, &tmQ, p.q_col0 + h * ATTN_HD, (2 * pr + 1) * 128, g, &item_full[b]);
-        tma_load_3d(buf + 2 * ATTN_Q_BYTES, &tmKV, p.k_col0 + h * ATTN_HD, 0, g, &item_full[b]);
-        tma_load_3d(buf + 2 * ATTN_Q_BYTES + kv_bytes, &tmKV, p.v_col0 + h * ATTN_HD, 0, g, &item_full[b]);
-        if (++b == 2) { b = 0; ph ^= 1; }
+        uint8_t* qbuf = q_smem + qb * q_bytes;
+        // window coordinates (windowed): g = image * nWin + wi * nJ + wj
+        int c3 = 0, c4 = 0;
+        if (WINDOWED) {
+          const int img = g / p.nWin, w = g - img * p.nWin;
+          c3 = w % p.nJ;                                  // window column
+          c4 = img * (p.nWin / p.nJ) + w / p.nJ;          // image * nI + window row
+        }
+        mbar_wait(&q_empty[qb], qph ^ 1);
+        if (WINDOWED) {
+          // whole window of Q (nkb boxes, window-token order), the MMA picks its 128-row tiles by offset
+          mbar_expect_tx(&q_full[qb], p.nkb * p.kb_rows * Cfg::ROW_BYTES);
+          for (int j = 0; j < p.nkb; ++j)
+            tma_load_5d(qbuf + j * p.kb_rows * Cfg::ROW_BYTES, &tmQ, p.q_col0 + h * HD, 0, c3, j * p.h_box, c4, &q_full[qb]);
+        } else {
+          const bool two = (2 * pr + 1) < p.q_tiles;
+          mbar_expect_tx(&q_full[qb], (two ? 2 : 1) * Cfg::Q_TILE_BYTES);
+          tma_load_3d(qbuf, &tmQ, p.q_col0 + h * HD, (2 * pr) * 128, g, &q_full[qb]);
+          if (two) tma_load_3d(qbuf + Cfg::Q_TILE_BYTES, &tmQ, p.q_col0 + h * HD, (2 * pr + 1) * 128, g, &q_full[qb]);
+        }
+        for (int j = 0; j < p.nkb; ++j) {
+          uint8_t* kbuf = kv_smem + st * 2 * kvb_bytes;
+          mbar_wait(&kv_empty[st], kph ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * p.kb_rows * Cfg::ROW_BYTES);
+          if (WINDOWED) {
+            tma_load_5d(kbuf, &tmK, p.k_col0 + h * HD, 0, c3, j * p.h_box, c4, &kv_full[st]);
+            tma_load_5d(kbuf + kvb_bytes, &tmV, p.v_col0 + h * HD, 0, c3, j * p.h_box, c4, &kv_full[st]);
+          } else {
+            tma_load_3d(kbuf, &tmK, p.k_col0 + h * HD, j * p.kb, g, &kv_full[st]);
+            tma_load_3d(kbuf + kvb_bytes, &tmV, p.v_col0 + h * HD, j * p.kb, g, &kv_full[st]);
+          }
+          if (++st == 2) { st = 0; kph ^= 1; }
+        }
+        if (++qb == 2) { qb = 0; qph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int b = 0;
-      uint32_t ph = 0;
-      uint32_t slot_ph[2] = {0, 0};
-      const int ksteps_o = p.kp / 16;
+      int qb = 0, st = 0;
+      uint32_t qph = 0, kph = 0;
+      uint32_t se_ph[2] = {0, 0};     // slot_empty phase (one completion per item and slot)
+      uint32_t pf_ph[2] = {0, 0};     // p_full phase (one completion per block and slot)
+      const int ksteps_o = p.kb / 16;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int pr = item % p.pairs;
         const int nslots = ((2 * pr + 1) < p.q_tiles) ? 2 : 1;
-        const uint32_t buf = smem_u32(smem + b * item_bytes);
-        mbar_wait(&item_full[b], ph);
+        const uint32_t qbuf = smem_u32(q_smem + qb * q_bytes);
+        mbar_wait(&q_full[qb], qph);
         tc_fence_after();
-        const uint64_t kdesc = make_sdesc(buf + 2 * ATTN_Q_BYTES, 16, 1024, PA_SWZ_128B);
-        for (int s = 0; s < nslots; ++s) {
-          mbar_wait(&slot_empty[s], slot_ph[s] ^ 1);
+        for (int j = 0; j < p.nkb; ++j) {
+          const uint32_t kbuf = smem_u32(kv_smem + st * 2 * kvb_bytes);
+          mbar_wait(&kv_full[st], kph);
           tc_fence_after();
-          const uint64_t qdesc = make_sdesc(buf + s * ATTN_Q_BYTES, 16, 1024, PA_SWZ_128B);
-          const uint32_t d = tmem_base + s * ATTN_SLOT_COLS;
+          const uint64_t kdesc = make_sdesc(kbuf, 16, Cfg::SBO, Cfg::SWZ);
+          for (int s = 0; s < nslots; ++s) {
+            if (j == 0) {
+              mbar_wait(&slot_empty[s], se_ph[s] ^ 1);
+              se_ph[s] ^= 1;
+              tc_fence_after();
+            }
+            const int tile = WINDOWED ? (2 * pr + s) : s;
+            const uint64_t qdesc = make_sdesc(qbuf + tile * Cfg::Q_TILE_BYTES, 16, Cfg::SBO, Cfg::SWZ);
+            const uint32_t d = tmem_base + s * ATTN_SLOT_COLS;
 #pragma unroll
-          for (int k = 0; k < ATTN_HD / 16; ++k) umma_ss(d, qdesc + 2 * k, kdesc + 2 * k, p.idesc_s, k != 0);
-          umma_commit(&s_full[s]);
-        }
-        for (int s = 0; s < nslots; ++s) {
-          mbar_wait(&p_full[s], slot_ph[s]);
-          tc_fence_after();
-          const uint32_t slot = tmem_base + s * ATTN_SLOT_COLS;
-          // V is [key][d] with d contiguous: MN-major B operand, 8-key groups are 1024 B apart (SBO)
-          const uint64_t vdesc = make_sdesc(buf + 2 * ATTN_Q_BYTES + kv_bytes, 1024, 1024, PA_SWZ_128B);
-          for (int k = 0; k < ksteps_o; ++k) {
-            // P: 16 fp16 keys = 8 TMEM columns per step; V: 16 keys = 2048 B = 128 x 16 B per step
-            umma_ts(slot + ATTN_O_COL, slot + 8 * k, vdesc + 128 * k, p.idesc_o, k != 0);
+            for (int k = 0; k < HD / 16; ++k) umma_ss(d, qdesc + 2 * k, kdesc + 2 * k, p.idesc_s, k != 0);
+            umma_commit(&s_full[s]);
           }
-          umma_commit(&o_full[s]);
-          slot_ph[s] ^= 1;
+          for (int s = 0; s < nslots; ++s) {
+            mbar_wait(&p_full[s], pf_ph[s]);
+            pf_ph[s] ^= 1;
+            tc_fence_after();
+            const uint32_t slot = tmem_base + s * ATTN_SLOT_COLS;
+            // V block is [key][d] with d contiguous: MN-major B operand; 8-key groups are SBO bytes apart
+            const uint64_t vdesc = make_sdesc(kbuf + kvb_bytes, Cfg::SBO, Cfg::SBO, Cfg::SWZ);
+            for (int k = 0; k < ksteps_o; ++k)
+              umma_ts(slot + Cfg::O_COL, slot + 8 * k, vdesc + Cfg::V_KSTEP * k, p.idesc_o, (j | k) != 0);
+            umma_commit(&o_full[s]);
+          }
+          umma_commit(&kv_empty[st]);
+          if (++st == 2) { st = 0; kph ^= 1; }
         }
-        umma_commit(&item_empty[b]);
-        if (++b == 2) { b = 0; ph ^= 1; }
+        umma_commit(&q_empty[qb]);
+        if (++qb == 2) { qb = 0; qph ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -147,92 +223,142 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int slot = (warp - 4) >> 2;
     const int q = warp & 3;
     const uint32_t t_slot = tmem_base + slot * ATTN_SLOT_COLS + ((uint32_t)(q * 32) << 16);
-    const int nchunks = (p.kp + 31) / 32;
+    const int nchunks = (p.kb + 31) / 32;
     const float sl2 = p.scale_log2e;
-    uint32_t ph = 0;
+    uint32_t sf_ph = 0, of_ph = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int pr = item % p.pairs;
       const int gh = item / p.pairs;
       const int h = gh % p.H, g = gh / p.H;
       const int qt = 2 * pr + slot;
-      if (qt >= p.q_tiles) continue;          // this slot is idle for the item (uniform over the warpgroup)
+      if (qt >= p.q_tiles) continue;          // slot idle for this item (uniform over the warpgroup)
       const int row = qt * 128 + q * 32 + lane;
-      const bool warp_active = (qt * 128 + q * 32) < p.n_q;   // some row of this warp is a real query
-      mbar_wait(&s_full[slot], ph);
-      tc_fence_after();
-      float sum = 1.f;
-      if (warp_active) {
-        // ---- pass 1: row max over the real keys
-        float mx = -INFINITY;
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_slot + c * 32, v);
-          tmem_ld_wait();
+      const bool warp_active = (qt * 128 + q * 32) < p.n_q;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < p.nkb; ++j) {
+        const int nvalid = min(p.kb_rows, p.n_k - j * p.kb_rows);    // real keys in this block
+        mbar_wait(&s_full[slot], sf_ph);
+        sf_ph ^= 1;
+        tc_fence_after();
+        float alpha = 1.f, m_new = m_run;
+        if (warp_active) {
+          // ---- pass 1: block row max
+          float mx = -INFINITY;
+          for (int c = 0; c < nchunks; ++c) {
+            uint32_t v[32];
+            tmem_ld32(t_slot + c * 32, v);
+            tmem_ld_wait();
+            if (c * 32 + 32 <= nvalid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = (c * 32 + i < p.n_k) ? __uint_as_float(v[i]) : -INFINITY;
-            mx = fmaxf(mx, x);
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < nvalid) ? __uint_as_float(v[i]) : -INFINITY);
+            }
+          }
+          m_new = fmaxf(m_run, mx);
+          alpha = ex2f((m_run - m_new) * sl2);      // 0 on the first block (m_run = -inf)
+        }
+        if (j > 0) {
+          // previous block's PV must have retired before O is rescaled / P overwritten
+          mbar_wait(&o_full[slot], of_ph);
+          of_ph ^= 1;
+          tc_fence_after();
+          if (warp_active) {
+#pragma unroll
+            for (int c = 0; c < HD; c += 16) {
+              uint32_t o[16];
+              tmem_ld16(t_slot + AttnCfg<HD>::O_COL + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(t_slot + AttnCfg<HD>::O_COL + c, o);
+            }
           }
         }
-        const float mxs = mx * sl2;
-        // ---- pass 2: p = exp2(s*scale*log2e - max), row sum, fp16 P written in place
-        sum = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_slot + c * 32, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
+        if (warp_active) {
+          // ---- pass 2: p = exp2((s - m) * scale*log2e), running sum, fp16 P in place
+          const float mxs = m_new * sl2;
+          float sum = 0.f;
+          for (int c = 0; c < nchunks; ++c) {
+            uint32_t v[32];
+            tmem_ld32(t_slot + c * 32, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+            if (c * 32 + 32 <= nvalid) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float x0 = (c * 32 + i < p.n_k) ? __uint_as_float(v[i]) : -INFINITY;
-            const float x1 = (c * 32 + i + 1 < p.n_k) ? __uint_as_float(v[i + 1]) : -INFINITY;
-            const float e0 = ex2f(fmaf(x0, sl2, -mxs));
-            const float e1 = ex2f(fmaf(x1, sl2, -mxs));
-            sum += e0 + e1;
-            pk[i >> 1] = pack_h2(e0, e1);
+              for (int i = 0; i < 32; i += 2) {
+                const float e0 = ex2f(fmaf(__uint_as_float(v[i]), sl2, -mxs));
+                const float e1 = ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -mxs));
+                sum += e0 + e1;
+                pk[i >> 1] = pack_h2(e0, e1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float e0 = (c * 32 + i < nvalid) ? ex2f(fmaf(__uint_as_float(v[i]), sl2, -mxs)) : 0.f;
+                const float e1 = (c * 32 + i + 1 < nvalid) ? ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -mxs)) : 0.f;
+                sum += e0 + e1;
+                pk[i >> 1] = pack_h2(e0, e1);
+              }
+            }
+            tmem_st16(t_slot + c * 16, pk);
           }
-          tmem_st16(t_slot + c * 16, pk);
+          tmem_st_wait();
+          l_run = l_run * alpha + sum;
+          m_run = m_new;
         }
-        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[slot]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[slot]);
 
-      // ---- epilogue: O / rowsum -> fp16 -> global
-      mbar_wait(&o_full[slot], ph);
+      // ---- epilogue: O / rowsum (+ LePE already in place) -> fp16 -> global
+      mbar_wait(&o_full[slot], of_ph);
+      of_ph ^= 1;
       tc_fence_after();
       if (warp_active) {
-        const float inv = 1.f / sum;
-        uint32_t v0[32], v1[32];
-        tmem_ld32(t_slot + ATTN_O_COL, v0);
-        tmem_ld32(t_slot + ATTN_O_COL + 32, v1);
+        const float inv = 1.f / l_run;
+        uint32_t v[HD];
+        tmem_ld32(t_slot + Cfg::O_COL, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        if (HD == 64) tmem_ld32(t_slot + Cfg::O_COL + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[HD - 32]));
         tmem_ld_wait();
         if (row < p.n_q) {
-          uint16_t* dst = reinterpret_cast<uint16_t*>(p.O) + (long long)g * p.o_group + (long long)row * p.ldo +
-                          p.o_col0 + h * ATTN_HD;
+          long long tok;
+          int grp;
+          if (WINDOWED) {
+            const int img = g / p.nWin, w = g - img * p.nWin;
+            const int wi = w / p.nJ, wj = w - wi * p.nJ;
+            const int r = row / p.W_sp, c = row - r * p.W_sp;
+            tok = (long long)(wi * p.H_sp + r) * p.R + wj * p.W_sp + c;
+            grp = img;
+          } else {
+            tok = row;
+            grp = g;
+          }
+          uint16_t* dst = reinterpret_cast<uint16_t*>(p.O) + (long long)grp * p.o_group + tok * p.ldo + p.o_col0 + h * HD;
           uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            d4[i] = make_uint4(pack_h2(__uint_as_float(v0[8 * i + 0]) * inv, __uint_as_float(v0[8 * i + 1]) * inv),
-                               pack_h2(__uint_as_float(v0[8 * i + 2]) * inv, __uint_as_float(v0[8 * i + 3]) * inv),
-                               pack_h2(__uint_as_float(v0[8 * i + 4]) * inv, __uint_as_float(v0[8 * i + 5]) * inv),
-                               pack_h2(__uint_as_float(v0[8 * i + 6]) * inv, __uint_as_float(v0[8 * i + 7]) * inv));
-          }
+          for (int i = 0; i < HD / 8; ++i) {
+            float f[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            d4[4 + i] =
-                make_uint4(pack_h2(__uint_as_float(v1[8 * i + 0]) * inv, __uint_as_float(v1[8 * i + 1]) * inv),
-                           pack_h2(__uint_as_float(v1[8 * i + 2]) * inv, __uint_as_float(v1[8 * i + 3]) * inv),
-                           pack_h2(__uint_as_float(v1[8 * i + 4]) * inv, __uint_as_float(v1[8 * i + 5]) * inv),
-                           pack_h2(__uint_as_float(v1[8 * i + 6]) * inv, __uint_as_float(v1[8 * i + 7]) * inv));
+            for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[8 * i + k]) * inv;
+            if (p.add_into_out) {
+              const uint4 old = d4[i];
+              const __half2* oh = reinterpret_cast<const __half2*>(&old);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                f[2 * k] += __low2float(oh[k]);
+                f[2 * k + 1] += __high2float(oh[k]);
+              }
+            }
+            d4[i] = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&slot_empty[slot]);
-      ph ^= 1;
     }
   }
 

@@ -24,6 +24,9 @@ struct GemmParams {
   const float* bias;       // fp32 bias or nullptr
   int bias_mode;           // 0 none, 1 per column n, 2 per row m
   int out_dtype;           // 0 fp16, 1 bf16, 2 fp32
+  const void* residual;    // optional [M, N] tensor added in the epilogue (16-bit or fp32), or nullptr
+  long long ldr, r_batch;
+  int res_dtype;
   uint32_t idesc;
 };
 
@@ -163,6 +166,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.bias_mode == 1) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __ldg(p.bias + col + i) : 0.f;
+        }
+        if (p.residual != nullptr && row_ok) {
+          const long long r_off = (long long)z * p.r_batch + (long long)row * p.ldr + col;
+          if (p.res_dtype == 2) {
+            const float* rp = reinterpret_cast<const float*>(p.residual) + r_off;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __ldg(rp + i) : 0.f;
+          } else if (p.res_dtype == 0) {
+            const __half* rp = reinterpret_cast<const __half*>(p.residual) + r_off;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __half2float(__ldg(rp + i)) : 0.f;
+          } else {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __bfloat162float(__ldg(rp + i)) : 0.f;
+          }
         }
         if (row_ok) {
           const bool full = (col + 32 <= p.N);

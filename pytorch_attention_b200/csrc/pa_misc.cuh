@@ -1,0 +1,371 @@
+// pa_misc.cuh — the HBM-bound pieces around the tensor-core stages: depthwise convolutions with folded eval-mode
+// BatchNorm (PVT spatial reduction, CvT projection front-end), LayerNorm (CSWin), LePE (CSWin), the small
+// channel-attention cores of XCiT, and a row copy.  All are coalesced / 16-byte vectorised along the channel axis.
+#pragma once
+#include "pa_ptx.cuh"
+
+namespace pa {
+
+// 16-bit element helpers (dtype: 0 fp16, 1 bf16)
+__device__ __forceinline__ float ld16(const void* p, long long i, int dtype) {
+  return dtype == 0 ? __half2float(reinterpret_cast<const __half*>(p)[i])
+                    : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, int dtype, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (dtype == 0) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      f[2 * i] = __low2float(h);
+      f[2 * i + 1] = __high2float(h);
+    } else {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      f[2 * i] = __low2float(h);
+      f[2 * i + 1] = __high2float(h);
+    }
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int dtype) {
+  uint4 u;
+  if (dtype == 0) {
+    u.x = pack_h2(f[0], f[1]); u.y = pack_h2(f[2], f[3]); u.z = pack_h2(f[4], f[5]); u.w = pack_h2(f[6], f[7]);
+  } else {
+    u.x = pack_bf2(f[0], f[1]); u.y = pack_bf2(f[2], f[3]); u.z = pack_bf2(f[4], f[5]); u.w = pack_bf2(f[6], f[7]);
+  }
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PVT spatial reduction (pvt.py:67-71, 77-78): depthwise conv k = stride = sr over the token image, eval BatchNorm
+// folded into (scale, shift):  out[b, i*Ws+j, c] = scale[c] * sum_{u,v} w[(u*sr+v), c] x[b, (sr*i+u)*W + sr*j+v, c] + shift[c]
+// One thread = 8 consecutive channels of one output token (16-byte loads, coalesced along C).
+struct SrParams {
+  const void* x; void* out;        // x [B, H*W, C] (dtype), out [B, Hs*Ws, C] fp16
+  const float* w;                  // [sr*sr, C] fp32 (transposed depthwise weight)
+  const float* scale; const float* shift;   // [C] fp32
+  int B, H, W, C, sr, Hs, Ws, dtype;
+};
+__global__ void sr_conv_bn_kernel(const SrParams p) {
+  const int cvec = p.C / 8;
+  const long long total = (long long)p.B * p.Hs * p.Ws * cvec;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvec);
+    long long t = idx / cvec;
+    const int j = (int)(t % p.Ws); t /= p.Ws;
+    const int i = (int)(t % p.Hs);
+    const int b = (int)(t / p.Hs);
+    const int c0 = cv * 8;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int u = 0; u < p.sr; ++u) {
+      const long long rowbase = ((long long)b * p.H * p.W + (long long)(p.sr * i + u) * p.W + p.sr * j) * p.C + c0;
+      for (int v = 0; v < p.sr; ++v) {
+        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + rowbase + (long long)v * p.C));
+        float xf[8];
+        unpack8(xv, p.dtype, xf);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + (long long)(u * p.sr + v) * p.C + c0));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + (long long)(u * p.sr + v) * p.C + c0 + 4));
+        acc[0] = fmaf(xf[0], w0.x, acc[0]); acc[1] = fmaf(xf[1], w0.y, acc[1]);
+        acc[2] = fmaf(xf[2], w0.z, acc[2]); acc[3] = fmaf(xf[3], w0.w, acc[3]);
+        acc[4] = fmaf(xf[4], w1.x, acc[4]); acc[5] = fmaf(xf[5], w1.y, acc[5]);
+        acc[6] = fmaf(xf[6], w1.z, acc[6]); acc[7] = fmaf(xf[7], w1.w, acc[7]);
+      }
+    }
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(acc[k], __ldg(p.scale + c0 + k), __ldg(p.shift + c0 + k));
+    const long long ob = ((long long)b * p.Hs * p.Ws + (long long)i * p.Ws + j) * p.C + c0;
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + ob) = pack8(o, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CvT front-end (cvt.py:55-57, 66): depthwise ks x ks conv (stride 1, zero pad) + eval BatchNorm on an NCHW map,
+// written TOKEN-major [B, H*W, C] fp16 so the 1x1 qkv conv becomes a plain K-major GEMM.
+// Block = (32 channels) x (32 pixels): NCHW reads are coalesced along pixels, the smem transpose makes the
+// token-major writes coalesced along channels.
+struct DwParams {
+  const void* x; void* out;        // x [B, C, H, W] (dtype), out [B, H*W, C] fp16
+  const float* w;                  // [C, ks*ks] fp32
+  const float* scale; const float* shift;   // folded conv-bias + BN: y = scale*conv + shift
+  int B, C, H, W, ks, dtype;
+};
+__global__ void dwconv_bn_to_tokens_kernel(const DwParams p) {
+  __shared__ float tile[32][33];
+  const int HW = p.H * p.W;
+  const int pix0 = blockIdx.x * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8 threads
+  const int pad = (p.ks - 1) / 2;
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int c = c0 + cc, pix = pix0 + tx;
+    float acc = 0.f;
+    if (c < p.C && pix < HW) {
+      const int r = pix / p.W, q = pix % p.W;
+      const long long base = ((long long)b * p.C + c) * HW;
+      for (int u = 0; u < p.ks; ++u) {
+        const int rr = r + u - pad;
+        if (rr < 0 || rr >= p.H) continue;
+        for (int v = 0; v < p.ks; ++v) {
+          const int qq = q + v - pad;
+          if (qq < 0 || qq >= p.W) continue;
+          acc = fmaf(ld16(p.x, base + (long long)rr * p.W + qq, p.dtype), __ldg(p.w + (long long)c * p.ks * p.ks + u * p.ks + v), acc);
+        }
+      }
+      acc = fmaf(acc, __ldg(p.scale + c), __ldg(p.shift + c));
+    }
+    tile[cc][tx] = acc;
+  }
+  __syncthreads();
+  for (int pp = ty; pp < 32; pp += 8) {
+    const int pix = pix0 + pp, c = c0 + tx;
+    if (pix < HW && c < p.C)
+      reinterpret_cast<__half*>(p.out)[((long long)b * HW + pix) * p.C + c] = __float2half_rn(tile[tx][pp]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the channel axis (CSWinBlock.norm1, cswin.py:184): one warp per token row, fp32 statistics,
+// two-pass (mean, then centred variance) like ATen's layer_norm.  Output fp16.
+struct LnParams {
+  const void* x; void* out; const float* gamma; const float* beta;
+  long long rows; int C, dtype; float eps;
+};
+__global__ void layernorm_kernel(const LnParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (row >= p.rows) return;
+  const uint16_t* xr = reinterpret_cast<const uint16_t*>(p.x) + row * p.C;
+  float s = 0.f;
+  for (int c = lane * 8; c < p.C; c += 256) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xr + c)), p.dtype, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += f[k];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / p.C;
+  float v = 0.f;
+  for (int c = lane * 8; c < p.C; c += 256) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xr + c)), p.dtype, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v = fmaf(f[k] - mean, f[k] - mean, v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = rsqrtf(v / p.C + p.eps);
+  for (int c = lane * 8; c < p.C; c += 256) {
+    float f[8], o8[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xr + c)), p.dtype, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o8[k] = fmaf((f[k] - mean) * rstd, __ldg(p.gamma + c + k), __ldg(p.beta + c + k));
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + row * p.C + c) = pack8(o8, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// XCA core (xcit.py:251-262) for one (batch, head): q,k,v are [N, 64] fp16 column slices of the qkv buffer.
+//   A[d,e] = softmax_e( temperature * <q[:,d], k[:,e]> / (max(|q[:,d]|,eps) max(|k[:,e]|,eps)) ),   O[n,d] = sum_e A[d,e] v[n,e]
+// 256 threads: thread (ty,tx) owns the 4x4 block A[4ty..][4tx..]; tokens streamed through smem in chunks.
+// L2 norms reduce over the token axis: per-thread partials + warp-shuffle/smem reduction.
+struct XcaParams {
+  const void* qkv; void* out; const float* temperature;
+  int B, N, C, H;
+};
+constexpr int XCA_CHUNK = 32;
+__global__ void __launch_bounds__(256) xca_core_kernel(const XcaParams p) {
+  __shared__ float sq[XCA_CHUNK][65], sk[XCA_CHUNK][65];
+  __shared__ float A[64][65];
+  __shared__ float qn[64], kn[64];
+  const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const long long ld = 3LL * p.C;
+  const __half* base = reinterpret_cast<const __half*>(p.qkv) + (long long)b * p.N * ld + h * 64;
+  float acc[4][4] = {};
+  float nq = 0.f, nk = 0.f;         // thread tid<64: sum of squares of column tid of q; 64<=tid<128: of k
+  for (int n0 = 0; n0 < p.N; n0 += XCA_CHUNK) {
+    for (int i = tid; i < XCA_CHUNK * 64; i += 256) {
+      const int r = i >> 6, c = i & 63;
+      const bool ok = (n0 + r) < p.N;
+      sq[r][c] = ok ? __half2float(base[(long long)(n0 + r) * ld + c]) : 0.f;
+      sk[r][c] = ok ? __half2float(base[(long long)(n0 + r) * ld + p.C + c]) : 0.f;
+    }
+    __syncthreads();
+    if (tid < 64) {
+      for (int r = 0; r < XCA_CHUNK; ++r) nq = fmaf(sq[r][tid], sq[r][tid], nq);
+    } else if (tid < 128) {
+      for (int r = 0; r < XCA_CHUNK; ++r) nk = fmaf(sk[r][tid - 64], sk[r][tid - 64], nk);
+    }
+    for (int r = 0; r < XCA_CHUNK; ++r) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sq[r][4 * ty + i]; bb[i] = sk[r][4 * tx + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  if (tid < 64) qn[tid] = fmaxf(sqrtf(nq), 1e-12f);            // F.normalize eps (xcit.py:255)
+  else if (tid < 128) kn[tid - 64] = fmaxf(sqrtf(nk), 1e-12f);
+  __syncthreads();
+  const float temp = __ldg(p.temperature + h);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) A[4 * ty + i][4 * tx + j] = acc[i][j] / (qn[4 * ty + i] * kn[4 * tx + j]) * temp;
+  __syncthreads();
+  // row softmax over e: 4 threads per row, shuffle reductions
+  {
+    const int row = tid >> 2, part = tid & 3;
+    float mx = -INFINITY;
+    for (int e = part; e < 64; e += 4) mx = fmaxf(mx, A[row][e]);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.f;
+    for (int e = part; e < 64; e += 4) { const float ex = __expf(A[row][e] - mx); A[row][e] = ex; sum += ex; }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = 1.f / sum;
+    for (int e = part; e < 64; e += 4) A[row][e] *= inv;
+  }
+  __syncthreads();
+  // O[n, d] = sum_e A[d][e] v[n][e]; v streamed through sq
+  __half* outb = reinterpret_cast<__half*>(p.out) + (long long)b * p.N * p.C + h * 64;
+  for (int n0 = 0; n0 < p.N; n0 += XCA_CHUNK) {
+    for (int i = tid; i < XCA_CHUNK * 64; i += 256) {
+      const int r = i >> 6, c = i & 63;
+      sq[r][c] = (n0 + r) < p.N ? __half2float(base[(long long)(n0 + r) * ld + 2 * p.C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < XCA_CHUNK * 64; i += 256) {
+      const int r = i >> 6, d = i & 63;
+      if (n0 + r < p.N) {
+        float o = 0.f;
+#pragma unroll 16
+        for (int e = 0; e < 64; ++e) o = fmaf(A[d][e], sq[r][e], o);
+        outb[(long long)(n0 + r) * p.C + d] = __float2half_rn(o);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ClassAttention core (xcit.py:180-185) for one (batch, head): only the CLS (token 0) query attends.
+struct ClsParams {
+  const void* qkv; void* out;    // qkv [B, N, 3C] fp16; out [B, C] fp16
+  int B, N, C, H; float scale;
+};
+__global__ void __launch_bounds__(256) class_attn_core_kernel(const ClsParams p) {
+  extern __shared__ float sc[];    // [N] scores
+  __shared__ float red[8];
+  __shared__ float q0[64];
+  const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long ld = 3LL * p.C;
+  const __half* base = reinterpret_cast<const __half*>(p.qkv) + (long long)b * p.N * ld + h * 64;
+  if (tid < 64) q0[tid] = __half2float(base[tid]);
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int n = tid; n < p.N; n += 256) {
+    const __half* kr = base + (long long)n * ld + p.C;
+    float s = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < 64; ++d) s = fmaf(q0[d], __half2float(kr[d]), s);
+    s *= p.scale;
+    sc[n] = s;
+    mx = fmaxf(mx, s);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int n = tid; n < p.N; n += 256) { const float e = __expf(sc[n] - mx); sc[n] = e; sum += e; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += red[w];
+  const float inv = 1.f / sum;
+  // cls[d] = sum_n a[n] v[n][d]: thread (part = tid/64, d = tid%64) strides over tokens, then reduce 4 parts
+  __shared__ float part[4][64];
+  {
+    const int d = tid & 63, pt = tid >> 6;
+    float o = 0.f;
+    for (int n = pt; n < p.N; n += 4) o = fmaf(sc[n], __half2float(base[(long long)n * ld + 2 * p.C + d]), o);
+    part[pt][d] = o;
+  }
+  __syncthreads();
+  if (tid < 64)
+    reinterpret_cast<__half*>(p.out)[(long long)b * p.C + h * 64 + tid] =
+        __float2half_rn((part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]) * inv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 16-byte vectorised copy (ClassAttention pass-through of the patch tokens, xcit.py:187)
+__global__ void copy16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __ldg(src + i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LePE (cswin.py:86-99): depthwise 3x3 over each cross-shaped window of V, zero padded AT WINDOW BORDERS,
+// written (fp16) into the attention output buffer at the image position of the token; the attention epilogue
+// then adds its softmax(QK^T)V on top.  v: column slice [v_col0, v_col0+Cb) of the [B, L, ldv] qkv buffer.
+struct LepeParams {
+  const void* v; void* out;       // out [B, L, ldo] fp16 at column o_col0
+  const float* w; const float* bias;   // [9, Cb] fp32 (transposed), [Cb]
+  long long ldv, ldo; int v_col0, o_col0;
+  int B, R, Cb, H_sp, W_sp;       // R = resolution (H = W = R)
+};
+__global__ void lepe_kernel(const LepeParams p) {
+  const int cvec = p.Cb / 8;
+  const long long total = (long long)p.B * p.R * p.R * cvec;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvec);
+    long long t = idx / cvec;
+    const int col = (int)(t % p.R); t /= p.R;
+    const int row = (int)(t % p.R);
+    const int b = (int)(t / p.R);
+    const int c0 = cv * 8;
+    const int r_in = row % p.H_sp, c_in = col % p.W_sp;     // position inside the window
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = __ldg(p.bias + c0 + k);
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int rr = r_in + u - 1;
+      if (rr < 0 || rr >= p.H_sp) continue;
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        const int cc = c_in + v - 1;
+        if (cc < 0 || cc >= p.W_sp) continue;
+        const long long tok = (long long)b * p.R * p.R + (long long)(row + u - 1) * p.R + (col + v - 1);
+        float xf[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.v) + tok * p.ldv + p.v_col0 + c0)), 0, xf);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + (u * 3 + v) * p.Cb + c0));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + (u * 3 + v) * p.Cb + c0 + 4));
+        acc[0] = fmaf(xf[0], w0.x, acc[0]); acc[1] = fmaf(xf[1], w0.y, acc[1]);
+        acc[2] = fmaf(xf[2], w0.z, acc[2]); acc[3] = fmaf(xf[3], w0.w, acc[3]);
+        acc[4] = fmaf(xf[4], w1.x, acc[4]); acc[5] = fmaf(xf[5], w1.y, acc[5]);
+        acc[6] = fmaf(xf[6], w1.z, acc[6]); acc[7] = fmaf(xf[7], w1.w, acc[7]);
+      }
+    }
+    const long long tok = (long long)b * p.R * p.R + (long long)row * p.R + col;
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + tok * p.ldo + p.o_col0 + c0) = pack8(acc, 0);
+  }
+}
+
+}  // namespace pa

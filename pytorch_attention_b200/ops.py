@@ -47,7 +47,7 @@ def workspace(nbytes, device):
     return buf
 
 
-def gemm_tn(a, b, bias=None, out=None, out_dtype=None, bias_mode=None, block_n=0):
+def gemm_tn(a, b, bias=None, out=None, out_dtype=None, bias_mode=None, block_n=0, residual=None):
     """out[z][m,n] = sum_k a[z][m,k] b[z][n,k] (+bias).  a: [M,K] or [Z,M,K]; b: [N,K] or [Z,N,K] (row pitch may
     exceed K); bias fp32 per column (default) or per row (bias_mode=2)."""
     require_cuda(a, b, bias, out)
@@ -74,12 +74,18 @@ def gemm_tn(a, b, bias=None, out=None, out_dtype=None, bias_mode=None, block_n=0
     g.bias = _ptr(bias)
     g.bias_mode = 0 if bias is None else (bias_mode or 1)
     g.block_n = block_n
+    if residual is not None:
+        require_cuda(residual)
+        assert residual.stride(-1) == 1 and residual.shape[-2:] == (M, N)
+        g.residual, g.ldr = _ptr(residual), residual.stride(-2)
+        g.r_batch = residual.stride(0) if residual.dim() == 3 else 0
+        g.res_dtype = dtype_code(residual.dtype)
     with torch.cuda.device(a.device):
         L.check(L.load().pa_gemm_tn(C.byref(g), stream_ptr(a.device)))
     return out
 
 
-def attn_core(q, kv, n_heads, scale, q_col0, k_col0, v_col0, out=None, o_col0=0):
+def attn_core(q, kv, n_heads, scale, q_col0, k_col0, v_col0, out=None, o_col0=0, head_dim=64):
     """q: [G, n_q, ldq] fp16, kv: [G, n_k, ldkv] fp16 (heads are 64-wide column slices starting at *_col0).
     Returns out [G, n_q, n_heads*64] fp16 (or writes into `out` at column o_col0)."""
     require_cuda(q, kv, out)
@@ -88,13 +94,27 @@ def attn_core(q, kv, n_heads, scale, q_col0, k_col0, v_col0, out=None, o_col0=0)
     G, n_q = q.shape[0], q.shape[1]
     n_k = kv.shape[1]
     if out is None:
-        out = torch.empty(G, n_q, n_heads * 64, dtype=torch.float16, device=q.device)
+        out = torch.empty(G, n_q, n_heads * head_dim, dtype=torch.float16, device=q.device)
     a = L.AttnArgs()
     a.G, a.H, a.n_q, a.n_k = G, n_heads, n_q, n_k
     a.q, a.ldq, a.q_group, a.q_col0 = _ptr(q), q.stride(1), q.stride(0), q_col0
     a.kv, a.ldkv, a.kv_group, a.k_col0, a.v_col0 = _ptr(kv), kv.stride(1), kv.stride(0), k_col0, v_col0
     a.o, a.ldo, a.o_group, a.o_col0 = _ptr(out), out.stride(1), out.stride(0), o_col0
     a.scale = float(scale)
+    a.head_dim = head_dim
     with torch.cuda.device(q.device):
         L.check(L.load().pa_attn_core(C.byref(a), stream_ptr(q.device)))
     return out
+
+
+def run_with_workspace(x, args, ws_fn, fwd_fn):
+    """Common tail of the module forwards: query the workspace size (0 = invalid arguments, let the entry point
+    report the error), fetch the cached workspace, launch on the current stream."""
+    import ctypes
+    lib = L.load()
+    with torch.cuda.device(x.device):
+        need = getattr(lib, ws_fn)(ctypes.byref(args))
+        if need == 0:
+            L.check(getattr(lib, fwd_fn)(ctypes.byref(args), None, 0, stream_ptr(x.device)))
+        ws = workspace(need, x.device)
+        L.check(getattr(lib, fwd_fn)(ctypes.byref(args), _ptr(ws), ws.numel(), stream_ptr(x.device)))

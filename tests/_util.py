@@ -32,3 +32,25 @@ def rel_fro(y, ref):
 def rel_max(y, ref):
     y, ref = y.double(), ref.double()
     return ((y - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+def build_dropin(spec, params, out_dtype=None):
+    """Instantiate the B200 drop-in for a golden/oracle case spec and load the reference state_dict into it."""
+    import pytorch_attention_b200 as pa
+    cls = {"vit": pa.vit.Attention, "pvt": pa.pvt.Attention, "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention,
+           "cswin_block": pa.cswin.CSWinBlock, "xca": pa.xcit.XCA, "class_attn": pa.xcit.ClassAttention}[spec["variant"]]
+    m = cls(**spec["ctor"]).eval()
+    m.load_state_dict(params)          # strict: keys and shapes must match the reference's
+    if hasattr(m, "out_dtype"):
+        m.out_dtype = out_dtype
+    return m
+
+
+def run_dropin(spec, m, x):
+    import torch
+    with torch.no_grad():
+        if spec["variant"] == "pvt":
+            return m(x, *spec["hw"])
+        if spec["variant"] == "cswin_block":
+            return m.attention_half(x)
+        return m(x)

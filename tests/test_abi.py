@@ -56,8 +56,33 @@ def test_gemm_and_attn_argument_validation_without_gpu():
     assert lib.pa_gemm_tn(C.byref(g), None) == L.PA_ERR_BAD_SHAPE      # K % 8
     at = L.AttnArgs()
     at.q = at.kv = at.o = 16
-    at.G, at.H, at.n_q, at.n_k, at.scale = 1, 1, 8, 300, 1.0
-    assert lib.pa_attn_core(C.byref(at), None) == L.PA_ERR_UNSUPPORTED  # n_k > 256
+    at.G, at.H, at.n_q, at.n_k, at.scale = 1, 1, 8, 300, -1.0
+    assert lib.pa_attn_core(C.byref(at), None) == L.PA_ERR_UNSUPPORTED  # scale must be > 0
+    at.scale, at.head_dim = 1.0, 48
+    assert lib.pa_attn_core(C.byref(at), None) == L.PA_ERR_UNSUPPORTED  # head_dim 48
+
+
+def test_variant_argument_validation_without_gpu():
+    lib = L.load()
+    p = L.PvtArgs()
+    p.B, p.N, p.C, p.H, p.Himg, p.Wimg, p.sr = 1, 64, 128, 3, 8, 8, 1
+    assert lib.pa_pvt_fwd(C.byref(p), None, 0, None) == L.PA_ERR_BAD_SHAPE          # 128 % 3 (pvt.py:56)
+    p.H, p.Himg = 2, 7
+    assert lib.pa_pvt_fwd(C.byref(p), None, 0, None) == L.PA_ERR_BAD_SHAPE          # N != H*W
+    le = L.LepeArgs()
+    le.B, le.L, le.C, le.H, le.resolution, le.idx, le.split_size = 1, 50, 64, 2, 7, 0, 7
+    assert lib.pa_cswin_lepe_fwd(C.byref(le), None) == L.PA_ERR_BAD_SHAPE           # L != resolution^2 (cswin.py:110)
+    assert b"wrong size" in lib.pa_last_error()
+    le.L, le.idx = 49, 2
+    assert lib.pa_cswin_lepe_fwd(C.byref(le), None) == L.PA_ERR_UNSUPPORTED         # ERROR MODE (cswin.py:68-70)
+    x = L.XcitArgs()
+    x.B, x.N, x.C, x.H = 1, 8, 128, 4
+    assert lib.pa_xca_fwd(C.byref(x), None, 0, None) == L.PA_ERR_UNSUPPORTED        # head_dim 32 on the XCA path
+    cv = L.CvtArgs()
+    assert lib.pa_cvt_fwd(C.byref(cv), None, 0, None) == L.PA_ERR_BAD_SHAPE
+    blk = L.CswinBlockArgs()
+    blk.B, blk.L, blk.C, blk.H, blk.reso, blk.split_size = 1, 100, 128, 4, 14, 7
+    assert lib.pa_cswin_block_attn_fwd(C.byref(blk), None, 0, None) == L.PA_ERR_BAD_SHAPE
 
 
 def test_python_error_mapping():

@@ -106,8 +106,9 @@ def test_vit_edge_shapes_and_errors():
     m = m.cuda()
     with torch.no_grad():
         assert rel_fro(m(x.cuda()).float().cpu(), ref) < TOL
-        with pytest.raises(ValueError):                 # N > 256 not supported by this kernel: explicit error
-            m(torch.randn(1, 300, 128, device="cuda").half())
+        xl = torch.randn(2, 600, 128).half()            # N > 256: key blocks + online softmax
+        refl = vit_attention(xl.float(), sd["qkv.weight"], sd["qkv.bias"], sd["proj.weight"], sd["proj.bias"], 2)
+        assert rel_fro(m(xl.cuda()).float().cpu(), refl) < TOL
         with pytest.raises(ValueError):
             m(torch.randn(1, 8, 128, device="cuda"))    # fp32 input
     with pytest.raises(NotImplementedError):
