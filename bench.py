@@ -288,17 +288,24 @@ def run_ours(args, rank, world, local):
             ybuf = torch.empty(RING, rows, C, dtype=torch.float16, device=dev)
             xf = [x.view(rows, C) for x in xs]
 
-            def timed(fn, iters=40):
-                for i in range(4):
+            def timed(fn, reps=6):
+                """One CUDA graph holding RING launches (one per ring slot), replayed `reps` times: device time only."""
+                for i in range(RING):
                     fn(i)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for i in range(RING):
+                        fn(i)
+                g.replay()
                 torch.cuda.synchronize()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                for i in range(iters):
-                    fn(i)
+                for _ in range(reps):
+                    g.replay()
                 b.record()
                 torch.cuda.synchronize()
-                return a.elapsed_time(b) / iters * 1e3
+                return a.elapsed_time(b) / (reps * RING) * 1e3
 
             kern["qkv_gemm_us"] = timed(lambda i: ops.gemm_tn(xf[i % RING], wq, out=qkv[i % RING]))
             kern["attn_core_us"] = timed(lambda i: ops.attn_core(qkv[i % RING].view(B, N, 3 * C), qkv[i % RING].view(B, N, 3 * C), H,

@@ -65,8 +65,11 @@ typedef struct {
   const void* residual;              /* optional tensor added to the result ([Z][M,N], pitch ldr), or NULL */
   long long ldr, r_batch;
   int res_dtype;                     /* F16/BF16/F32 */
+  int cluster;                       /* 0 = auto; 1/2/4: CTAs per cluster sharing the B tile by TMA multicast; -2: CTA pairs (tcgen05 cta_group::2) */
 } pa_gemm_args;
 int pa_gemm_tn(const pa_gemm_args* a, void* stream);
+/* debug aid: CTA 0 of later GEMM launches writes per-tile clock64 stamps into this device buffer (>= 4 KiB); NULL turns it off */
+void pa_debug_set_gemm_trace(void* device_buffer);
 
 /* O[g][i, h*64+d] = sum_j softmax_j(scale * Q[g][i,h,:].K[g][j,h,:]) V[g][j,h,d];  fp16 in, fp16 out, head_dim 64,
  * any n_k

@@ -22,7 +22,7 @@ class GemmArgs(C.Structure):
                 ("B", _vp), ("ldb", _ll), ("b_batch", _ll),
                 ("D", _vp), ("ldd", _ll), ("d_batch", _ll),
                 ("bias", _vp), ("bias_mode", _i), ("block_n", _i),
-                ("residual", _vp), ("ldr", _ll), ("r_batch", _ll), ("res_dtype", _i)]
+                ("residual", _vp), ("ldr", _ll), ("r_batch", _ll), ("res_dtype", _i), ("cluster", _i)]
 
 
 class AttnArgs(C.Structure):
@@ -85,6 +85,7 @@ SYMBOLS = {
     "pa_device_check": (_i, [_i]),
     "pa_launch_count": (C.c_ulonglong, []),
     "pa_gemm_tn": (_i, [C.POINTER(GemmArgs), _vp]),
+    "pa_debug_set_gemm_trace": (None, [_vp]),
     "pa_attn_core": (_i, [C.POINTER(AttnArgs), _vp]),
     "pa_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitArgs)]),
     "pa_vit_fwd": (_i, [C.POINTER(VitArgs), _vp, C.c_size_t, _vp]),

@@ -26,22 +26,55 @@ struct Arena {
 };
 
 // ------------------------------------------------------------------------------------------------ GEMM
-template <int BN, int ST>
-int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, ST>;
+template <int BN, int ST, int CL, bool PAIR = false>
+int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, GemmParams p, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, ST, PAIR>;
   static bool attr_done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    PA_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PA_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<BN, ST, CL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done[dev & 63] = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles * p.Z;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tn_kernel<BN, ST><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
-  PA_CUDA_OK(cudaGetLastError());
+  p.m_groups = (p.m_tiles + CL - 1) / CL;
+  const int supertiles = p.m_groups * p.n_tiles * p.Z;
+  const int max_clusters = num_sms() / CL;
+  const int nclusters = supertiles < max_clusters ? supertiles : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * CL);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  PA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, ST, CL, PAIR>, tmA, tmB, tmD, p));
   launch_counter()++;
   return PA_OK;
+}
+
+template <int BN, int ST>
+int launch_gemm_cl(int cl, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const GemmParams& p,
+                   cudaStream_t st) {
+  if (cl == -2) return launch_gemm_cfg<BN, (ST * (128 + BN) * 128) / ((128 + BN / 2) * 128) < 8 ? (ST * (128 + BN)) / (128 + BN / 2) : 8, 2, true>(tmA, tmB, tmD, p, st);
+  if (cl == 4) return launch_gemm_cfg<BN, ST, 4>(tmA, tmB, tmD, p, st);
+  if (cl == 2) return launch_gemm_cfg<BN, ST, 2>(tmA, tmB, tmD, p, st);
+  return launch_gemm_cfg<BN, ST, 1>(tmA, tmB, tmD, p, st);
+}
+
+long long* g_gemm_trace = nullptr;   // debug hook, see pa_debug_set_gemm_trace
+
+int pick_cluster(int m_tiles) {
+  const char* env = getenv("PA_GEMM_CLUSTER");
+  if (env) {
+    int v = atoi(env);
+    if (v == 1 || v == 2 || v == 4 || v == -2) return v;
+  }
+  return m_tiles >= 2 ? -2 : 1;
 }
 
 int pick_block_n(int M, int N, int K, int Z) {
@@ -81,6 +114,11 @@ int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
   if (rc) return rc;
 
   int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, a->K, a->Z);
+  int cl = a->cluster ? a->cluster : pick_cluster((a->M + 127) / 128);
+  if (cl != 1 && cl != 2 && cl != 4 && cl != -2) return fail(PA_ERR_UNSUPPORTED, "pa_gemm_tn: cluster %d not in {1,2,4,-2}", cl);
+  if (bn == 96 && cl == 4) cl = 2;          // B slices must stay whole 8-row swizzle atoms
+  const bool pair = (cl == -2);             // cta_group::2: CTA pairs, 256-row tiles, each CTA stages half of B
+  const int b_box_rows = pair ? bn / 2 : bn / cl;
   CUtensorMap tmA, tmB;
   {
     const int za = a->a_batch ? a->Z : 1;
@@ -94,7 +132,7 @@ int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
     const int zb = a->b_batch ? a->Z : 1;
     uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->N, (uint64_t)zb};
     uint64_t str[2] = {(uint64_t)a->ldb * 2, (uint64_t)(a->b_batch ? a->b_batch : (long long)a->ldb * a->N) * 2};
-    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    uint32_t box[3] = {64, (uint32_t)b_box_rows, 1};
     rc = make_tmap_16b(&tmB, a->b_dtype, a->B, 3, dims, str, box);
     if (rc) return rc;
   }
@@ -107,13 +145,27 @@ int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
   p.D = a->D; p.ldd = a->ldd; p.d_batch = a->d_batch;
   p.bias = a->bias; p.bias_mode = a->bias_mode; p.out_dtype = a->out_dtype;
   p.residual = a->residual; p.ldr = a->ldr; p.r_batch = a->r_batch; p.res_dtype = a->res_dtype;
-  p.idesc = make_idesc(128, bn, a->a_dtype, a->b_dtype, 0, 0);
+  p.idesc = make_idesc(pair ? 256 : 128, bn, a->a_dtype, a->b_dtype, 0, 0);
+  p.trace = g_gemm_trace;
+  { const char* dbg = getenv("PA_GEMM_DEBUG"); p.debug_flags = dbg ? atoi(dbg) : 0; }
+  // output map for the staged TMA-store epilogue (128 x 32 sub-tiles); needs 16-byte aligned base and pitches
+  const int elt = a->out_dtype == PA_DTYPE_F32 ? 4 : 2;
+  p.tma_store = ((reinterpret_cast<uintptr_t>(a->D) & 15) == 0) && ((a->ldd * elt) % 16 == 0) &&
+                (a->Z == 1 || (a->d_batch * elt) % 16 == 0) && !getenv("PA_GEMM_DIRECT_STORE");
+  CUtensorMap tmD = tmA;
+  if (p.tma_store) {
+    uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->Z};
+    uint64_t str[2] = {(uint64_t)a->ldd * elt, (uint64_t)(a->Z > 1 ? a->d_batch : a->ldd * (long long)a->M) * elt};
+    uint32_t box[3] = {32, 128, 1};
+    rc = make_tmap_16b(&tmD, a->out_dtype, a->D, 3, dims, str, box, elt == 4 ? TM_SWZ_128 : TM_SWZ_64);
+    if (rc) return rc;
+  }
   switch (bn) {
-    case 256: return launch_gemm_cfg<256, 4>(tmA, tmB, p, st);
-    case 192: return launch_gemm_cfg<192, 5>(tmA, tmB, p, st);
-    case 128: return launch_gemm_cfg<128, 6>(tmA, tmB, p, st);
-    case 96:  return launch_gemm_cfg<96, 7>(tmA, tmB, p, st);
-    case 64:  return launch_gemm_cfg<64, 8>(tmA, tmB, p, st);
+    case 256: return launch_gemm_cl<256, 4>(cl, tmA, tmB, tmD, p, st);
+    case 192: return launch_gemm_cl<192, 4>(cl, tmA, tmB, tmD, p, st);
+    case 128: return launch_gemm_cl<128, 6>(cl, tmA, tmB, tmD, p, st);
+    case 96:  return launch_gemm_cl<96, 6>(cl, tmA, tmB, tmD, p, st);
+    case 64:  return launch_gemm_cl<64, 8>(cl, tmA, tmB, tmD, p, st);
     default: return fail(PA_ERR_UNSUPPORTED, "pa_gemm_tn: block_n %d not in {64,96,128,192,256}", bn);
   }
 }
@@ -278,6 +330,9 @@ int pa_device_check(int device) {
   if (major != 10) return fail(PA_ERR_DEVICE, "device %d is compute capability %d.x; sm_100 (B200) required", device, major);
   return PA_OK;
 }
+
+/* debug: device buffer of >= 64*8 int64 that CTA 0 of every later GEMM launch fills with clock64 stamps (NULL = off) */
+void pa_debug_set_gemm_trace(void* device_buffer) { g_gemm_trace = reinterpret_cast<long long*>(device_buffer); }
 
 int pa_gemm_tn(const pa_gemm_args* a, void* stream) { return gemm_impl(a, (cudaStream_t)stream); }
 int pa_attn_core(const pa_attn_args* a, void* stream) { return attn_impl(a, (cudaStream_t)stream); }

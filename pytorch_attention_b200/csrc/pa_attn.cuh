@@ -124,23 +124,23 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int qb = 0, st = 0;
-      uint32_t qph = 0, kph = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        const int pr = item % p.pairs;
-        const int gh = item / p.pairs;
-        const int h = gh % p.H, g = gh / p.H;
-        uint8_t* qbuf = q_smem + qb * q_bytes;
-        // window coordinates (windowed): g = image * nWin + wi * nJ + wj
-        int c3 = 0, c4 = 0;
-        if (WINDOWED) {
-          const int img = g / p.nWin, w = g - img * p.nWin;
-          c3 = w % p.nJ;                                  // window column
-          c4 = img * (p.nWin / p.nJ) + w / p.nJ;          // image * nI + window row
-        }
-        mbar_wait(&q_empty[qb], qph ^ 1);
+    // ===================== TMA producer (warp converged; one elected lane issues) =====================
+    int qb = 0, st = 0;
+    uint32_t qph = 0, kph = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int pr = item % p.pairs;
+      const int gh = item / p.pairs;
+      const int h = gh % p.H, g = gh / p.H;
+      uint8_t* qbuf = q_smem + qb * q_bytes;
+      // window coordinates (windowed): g = image * nWin + wi * nJ + wj
+      int c3 = 0, c4 = 0;
+      if (WINDOWED) {
+        const int img = g / p.nWin, w = g - img * p.nWin;
+        c3 = w % p.nJ;                                  // window column
+        c4 = img * (p.nWin / p.nJ) + w / p.nJ;          // image * nI + window row
+      }
+      mbar_wait(&q_empty[qb], qph ^ 1);
+      if (elect_one()) {
         if (WINDOWED) {
           // whole window of Q (nkb boxes, window-token order), the MMA picks its 128-row tiles by offset
           mbar_expect_tx(&q_full[qb], p.nkb * p.kb_rows * Cfg::ROW_BYTES);
@@ -152,9 +152,12 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tma_load_3d(qbuf, &tmQ, p.q_col0 + h * HD, (2 * pr) * 128, g, &q_full[qb]);
           if (two) tma_load_3d(qbuf + Cfg::Q_TILE_BYTES, &tmQ, p.q_col0 + h * HD, (2 * pr + 1) * 128, g, &q_full[qb]);
         }
-        for (int j = 0; j < p.nkb; ++j) {
-          uint8_t* kbuf = kv_smem + st * 2 * kvb_bytes;
-          mbar_wait(&kv_empty[st], kph ^ 1);
+      }
+      __syncwarp();
+      for (int j = 0; j < p.nkb; ++j) {
+        uint8_t* kbuf = kv_smem + st * 2 * kvb_bytes;
+        mbar_wait(&kv_empty[st], kph ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&kv_full[st], 2 * p.kb_rows * Cfg::ROW_BYTES);
           if (WINDOWED) {
             tma_load_5d(kbuf, &tmK, p.k_col0 + h * HD, 0, c3, j * p.h_box, c4, &kv_full[st]);
@@ -163,60 +166,68 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tma_load_3d(kbuf, &tmK, p.k_col0 + h * HD, j * p.kb, g, &kv_full[st]);
             tma_load_3d(kbuf + kvb_bytes, &tmV, p.v_col0 + h * HD, j * p.kb, g, &kv_full[st]);
           }
-          if (++st == 2) { st = 0; kph ^= 1; }
         }
-        if (++qb == 2) { qb = 0; qph ^= 1; }
+        __syncwarp();
+        if (++st == 2) { st = 0; kph ^= 1; }
       }
+      if (++qb == 2) { qb = 0; qph ^= 1; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int qb = 0, st = 0;
-      uint32_t qph = 0, kph = 0;
-      uint32_t se_ph[2] = {0, 0};     // slot_empty phase (one completion per item and slot)
-      uint32_t pf_ph[2] = {0, 0};     // p_full phase (one completion per block and slot)
-      const int ksteps_o = p.kb / 16;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        const int pr = item % p.pairs;
-        const int nslots = ((2 * pr + 1) < p.q_tiles) ? 2 : 1;
-        const uint32_t qbuf = smem_u32(q_smem + qb * q_bytes);
-        mbar_wait(&q_full[qb], qph);
+    // ===================== MMA issuer (warp converged; one elected lane issues) =====================
+    int qb = 0, st = 0;
+    uint32_t qph = 0, kph = 0;
+    uint32_t se_ph0 = 0, se_ph1 = 0;     // slot_empty phase (one completion per item and slot)
+    uint32_t pf_ph0 = 0, pf_ph1 = 0;     // p_full phase (one completion per block and slot)
+    const int ksteps_o = p.kb / 16;
+    const uint32_t q_base = smem_u32(q_smem), kv_base = smem_u32(kv_smem);
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int pr = item % p.pairs;
+      const int nslots = ((2 * pr + 1) < p.q_tiles) ? 2 : 1;
+      const uint32_t qbuf = q_base + qb * q_bytes;
+      mbar_wait(&q_full[qb], qph);
+      tc_fence_after();
+      for (int j = 0; j < p.nkb; ++j) {
+        const uint32_t kbuf = kv_base + st * 2 * kvb_bytes;
+        mbar_wait(&kv_full[st], kph);
         tc_fence_after();
-        for (int j = 0; j < p.nkb; ++j) {
-          const uint32_t kbuf = smem_u32(kv_smem + st * 2 * kvb_bytes);
-          mbar_wait(&kv_full[st], kph);
-          tc_fence_after();
-          const uint64_t kdesc = make_sdesc(kbuf, 16, Cfg::SBO, Cfg::SWZ);
-          for (int s = 0; s < nslots; ++s) {
-            if (j == 0) {
-              mbar_wait(&slot_empty[s], se_ph[s] ^ 1);
-              se_ph[s] ^= 1;
-              tc_fence_after();
-            }
-            const int tile = WINDOWED ? (2 * pr + s) : s;
-            const uint64_t qdesc = make_sdesc(qbuf + tile * Cfg::Q_TILE_BYTES, 16, Cfg::SBO, Cfg::SWZ);
-            const uint32_t d = tmem_base + s * ATTN_SLOT_COLS;
+        const uint64_t kdesc = make_sdesc(kbuf, 16, Cfg::SBO, Cfg::SWZ);
+        for (int s = 0; s < nslots; ++s) {
+          if (j == 0) {
+            mbar_wait(&slot_empty[s], (s ? se_ph1 : se_ph0) ^ 1);
+            if (s) se_ph1 ^= 1; else se_ph0 ^= 1;
+            tc_fence_after();
+          }
+          const int tile = WINDOWED ? (2 * pr + s) : s;
+          const uint64_t qdesc = make_sdesc(qbuf + tile * Cfg::Q_TILE_BYTES, 16, Cfg::SBO, Cfg::SWZ);
+          const uint32_t d = tmem_base + s * ATTN_SLOT_COLS;
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < HD / 16; ++k) umma_ss(d, qdesc + 2 * k, kdesc + 2 * k, p.idesc_s, k != 0);
             umma_commit(&s_full[s]);
           }
-          for (int s = 0; s < nslots; ++s) {
-            mbar_wait(&p_full[s], pf_ph[s]);
-            pf_ph[s] ^= 1;
-            tc_fence_after();
-            const uint32_t slot = tmem_base + s * ATTN_SLOT_COLS;
-            // V block is [key][d] with d contiguous: MN-major B operand; 8-key groups are SBO bytes apart
-            const uint64_t vdesc = make_sdesc(kbuf + kvb_bytes, Cfg::SBO, Cfg::SBO, Cfg::SWZ);
+          __syncwarp();
+        }
+        for (int s = 0; s < nslots; ++s) {
+          mbar_wait(&p_full[s], s ? pf_ph1 : pf_ph0);
+          if (s) pf_ph1 ^= 1; else pf_ph0 ^= 1;
+          tc_fence_after();
+          const uint32_t slot = tmem_base + s * ATTN_SLOT_COLS;
+          // V block is [key][d] with d contiguous: MN-major B operand; 8-key groups are SBO bytes apart
+          const uint64_t vdesc = make_sdesc(kbuf + kvb_bytes, Cfg::SBO, Cfg::SBO, Cfg::SWZ);
+          if (elect_one()) {
             for (int k = 0; k < ksteps_o; ++k)
               umma_ts(slot + Cfg::O_COL, slot + 8 * k, vdesc + Cfg::V_KSTEP * k, p.idesc_o, (j | k) != 0);
             umma_commit(&o_full[s]);
+            if (s == nslots - 1) {
+              umma_commit(&kv_empty[st]);
+              if (j == p.nkb - 1) umma_commit(&q_empty[qb]);
+            }
           }
-          umma_commit(&kv_empty[st]);
-          if (++st == 2) { st = 0; kph ^= 1; }
+          __syncwarp();
         }
-        umma_commit(&q_empty[qb]);
-        if (++qb == 2) { qb = 0; qph ^= 1; }
+        if (++st == 2) { st = 0; kph ^= 1; }
       }
+      if (++qb == 2) { qb = 0; qph ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================== softmax + epilogue warpgroups =====================

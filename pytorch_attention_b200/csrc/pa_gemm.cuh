@@ -1,14 +1,16 @@
 // pa_gemm.cuh — persistent warp-specialised tcgen05 GEMM for the projection stages.
 //
-//   D[z][m, n] = sum_k A[z][m, k] * B[z][n, k]  (+ bias)      A, B K-major ("TN", nn.Linear layout)
+//   D[z][m, n] = sum_k A[z][m, k] * B[z][n, k]  (+ bias) (+ residual)      A, B K-major ("TN", nn.Linear layout)
 //
 // One CTA per SM, 256 threads:
 //   warp 0   TMA producer      (cp.async.bulk.tensor, 128B-swizzled 64-wide K blocks, STAGES-deep ring)
 //   warp 1   MMA issuer        (one thread: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16)
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue         (tcgen05.ld 32x32b -> bias -> convert -> global), double-buffered TMEM accumulator
+//   warps 4-7 epilogue         tcgen05.ld 32x32b -> bias/residual -> convert -> swizzled smem staging -> TMA bulk store
+//                              (coalesced, asynchronous; double-buffered TMEM accumulator so it overlaps the next mainloop).
+//                              Outputs whose row pitch is not a multiple of 16 B fall back to direct global stores.
 // Tiles are distributed round-robin over the persistent grid; rows beyond M / K are zero-filled by TMA
-// (3-D tensor maps {K, rows, Z}) and masked in the epilogue, so M, N need not divide the tile.
+// (3-D tensor maps {K, rows, Z}); the TMA store clips at the tensor edge, so M, N need not divide the tile.
 #pragma once
 #include "pa_ptx.cuh"
 
@@ -17,6 +19,7 @@ namespace pa {
 struct GemmParams {
   int M, N, K, Z;          // per-batch problem, Z batches
   int m_tiles, n_tiles;    // ceil(M/128), ceil(N/BLOCK_N)
+  int m_groups;            // ceil(m_tiles / CLUSTER): a cluster works on CLUSTER adjacent m-tiles of one n-tile
   int a_batched, b_batched;  // 1: operand has a batch (z) coordinate, 0: shared across z
   void* D;
   long long ldd;           // row pitch of D in elements
@@ -27,28 +30,55 @@ struct GemmParams {
   const void* residual;    // optional [M, N] tensor added in the epilogue (16-bit or fp32), or nullptr
   long long ldr, r_batch;
   int res_dtype;
+  int tma_store;           // 1: epilogue goes through smem + TMA store (tmD valid)
   uint32_t idesc;
+  long long* trace;        // debug: per-tile clock64 stamps of CTA 0 ([tile][8]), or nullptr
+  int debug_flags;         // debug experiments (env PA_GEMM_DEBUG): 1 = skip epilogue body
 };
+
+// trace slots: 0 kernel start | 1 first MMA of tile issued (tempty ok) | 2 first full barrier of tile passed
+//              3 last MMA of tile issued | 4 epilogue: accumulator ready | 5 epilogue: tile drained | 6 producer: first load of tile issued
+__device__ __forceinline__ void trace_stamp(const GemmParams& p, int tile_seq, int slot) {
+  if (p.trace != nullptr && blockIdx.x == 0 && tile_seq < 64) p.trace[tile_seq * 8 + slot] = clock64();
+}
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_CSTAGE_BYTES = 128 * 32 * 4;   // one 128 x 32 output sub-tile in fp32 (16-bit uses half)
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool PAIR = false>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;   // 16 KB
-  static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;       // cta_group::2: each CTA stages half of the B tile
+  static constexpr int B_BYTES = B_ROWS * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int C_OFFSET = STAGES * STAGE_BYTES;             // 2 output staging buffers
+  static constexpr int BAR_OFFSET = C_OFFSET + 2 * GEMM_CSTAGE_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;        // + barriers + 1024-alignment slack
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
 };
 
-template <int BLOCK_N, int STAGES>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// CLUSTER > 1: the CTAs of a cluster take adjacent m-tiles of the same n-tile; each loads 1/CLUSTER of the B tile and
+// TMA-multicasts it to all of them (L2->SM traffic per flop drops from (128+BN) to (128+BN/CLUSTER) rows per k-block).
+// A stage may be refilled only after EVERY CTA's MMAs have read it: the consumer release is a multicast commit.
+//
+// PAIR (requires CLUSTER == 2): tcgen05 cta_group::2.  The two CTAs of a cluster form one 256 x BLOCK_N tile: each stages
+// its own 128 rows of A and HALF of the B tile, the leader (rank 0) issues M=256 MMAs that read both CTAs' shared memory
+// and write both CTAs' TMEM.  Shared-memory traffic per flop drops by a third versus two independent 128 x BLOCK_N CTAs
+// (the 1-CTA kernel is capped at 128/192 = 67 % of the tensor pipe by TMA-write + MMA-read shared-memory bandwidth).
+//   full[stage]   leader's barrier, expect_tx = bytes of BOTH CTAs (every TMA load signals the leader's barrier)
+//   empty[stage]  each CTA's own barrier, released by the leader's multicast tcgen05.commit
+//   tfull[acc]    each CTA's own barrier (multicast commit);  tempty[acc]: leader's, 8 arrivals (4 epilogue warps x 2 CTAs)
+template <int BLOCK_N, int STAGES, int CLUSTER, bool PAIR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, STAGES>;
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+  static_assert(!PAIR || CLUSTER == 2, "cta_group::2 needs a cluster of exactly two CTAs");
+  using Cfg = GemmCfg<BLOCK_N, STAGES, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFFSET);
@@ -60,106 +90,150 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
-  const int tiles_per_z = p.m_tiles * p.n_tiles;
+  const int tiles_per_z = p.m_groups * p.n_tiles;        // super-tiles (CLUSTER m-tiles x 1 n-tile) per batch
   const int num_tiles = tiles_per_z * p.Z;
+  const int crank = (CLUSTER > 1) ? (int)cluster_ctarank() : 0;
+  const int cid = blockIdx.x / CLUSTER;                  // cluster index = persistent worker index
+  const int ncl = gridDim.x / CLUSTER;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CLUSTER) - 1);
+  constexpr int B_SLICE_ROWS = BLOCK_N / CLUSTER;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmD);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], PAIR ? 1 : CLUSTER);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], PAIR ? 8 : 4);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc2(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();     // peers' barriers must be initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int z = tile / tiles_per_z;
-        const int r = tile - z * tiles_per_z;
-        const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          tma_load_3d(sa, &tmA, kb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M, p.a_batched ? z : 0, &full_bar[stage]);
-          tma_load_3d(sb, &tmB, kb * GEMM_BLOCK_K, nt * BLOCK_N, p.b_batched ? z : 0, &full_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+    int stage = 0, tseq = 0;
+    uint32_t phase = 0;
+    if (lane == 0) trace_stamp(p, 0, 0);
+    for (int tile = cid; tile < num_tiles; tile += ncl, ++tseq) {
+      const int z = tile / tiles_per_z;
+      const int r = tile - z * tiles_per_z;
+      const int mg = r / p.n_tiles, nt = r - mg * p.n_tiles;
+      const int mt = mg * CLUSTER + crank;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        if (elect_one()) {
+          if (kb == 0) trace_stamp(p, tseq, 6);
+          if (PAIR) {
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_3d_2sm(sa, &tmA, kb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M, p.a_batched ? z : 0, &full_bar[stage]);
+            tma_load_3d_2sm(sb, &tmB, kb * GEMM_BLOCK_K, nt * BLOCK_N + crank * Cfg::B_ROWS, p.b_batched ? z : 0, &full_bar[stage]);
+          } else {
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_3d(sa, &tmA, kb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M, p.a_batched ? z : 0, &full_bar[stage]);
+            if (CLUSTER == 1) {
+              tma_load_3d(sb, &tmB, kb * GEMM_BLOCK_K, nt * BLOCK_N, p.b_batched ? z : 0, &full_bar[stage]);
+            } else {
+              tma_load_3d_mc(sb + crank * B_SLICE_ROWS * 128, &tmB, kb * GEMM_BLOCK_K, nt * BLOCK_N + crank * B_SLICE_ROWS,
+                             p.b_batched ? z : 0, &full_bar[stage], CMASK);
+            }
+          }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0;
+    // ===================== MMA issuer (PAIR: leader CTA only; whole warp converged, one elected lane issues) ============
+    if (!PAIR || crank == 0) {
+      int stage = 0, tseq = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const uint32_t smem_base = smem_u32(smem);
+      for (int tile = cid; tile < num_tiles; tile += ncl, ++tseq) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (lane == 0) trace_stamp(p, tseq, 1);
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          if (lane == 0 && kb == 0) trace_stamp(p, tseq, 2);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint64_t adesc = make_sdesc(sa, 16, 1024, PA_SWZ_128B);
           const uint64_t bdesc = make_sdesc(sa + Cfg::A_BYTES, 16, 1024, PA_SWZ_128B);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-            // advance 16 elements (32 bytes) along K inside the 128B swizzle atom: +2 in 16-byte units
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) != 0);
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+              // advance 16 elements (32 bytes) along K inside the 128B swizzle atom: +2 in 16-byte units
+              if (PAIR) umma_ss2(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) != 0);
+              else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) != 0);
+            }
+            // frees the smem stage (in every CTA that multicasts into it / is read by the pair MMA) when these MMAs retire
+            if (PAIR) umma_commit2_mc(&empty_bar[stage], CMASK);
+            else if (CLUSTER == 1) umma_commit(&empty_bar[stage]);
+            else umma_commit_mc(&empty_bar[stage], CMASK);
+            if (kb == num_kb - 1) {            // accumulator complete (PAIR: both CTAs' epilogues)
+              if (PAIR) umma_commit2_mc(&tfull_bar[acc], CMASK);
+              else umma_commit(&tfull_bar[acc]);
+            }
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);       // accumulator complete
+        if (lane == 0) trace_stamp(p, tseq, 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    int acc = 0;
+    const int trow = q * 32 + lane;         // row inside the tile
+    const bool leader = (warp == 4 && lane == 0);
+    const int elt = (p.out_dtype == 2) ? 4 : 2;
+    const int row_bytes = 32 * elt;         // staged sub-tile row: 128 B (fp32, SW128) or 64 B (16-bit, SW64)
+    uint8_t* cbuf = smem + Cfg::C_OFFSET;
+    int acc = 0, cb = 0, tseq = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = cid; tile < num_tiles; tile += ncl, ++tseq) {
       const int z = tile / tiles_per_z;
       const int r = tile - z * tiles_per_z;
-      const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
-      const int row = mt * GEMM_BLOCK_M + q * 32 + lane;
+      const int mg = r / p.n_tiles, nt = r - mg * p.n_tiles;
+      const int mt = mg * CLUSTER + crank;
+      const int row = mt * GEMM_BLOCK_M + trow;
       const int col0 = nt * BLOCK_N;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (leader) trace_stamp(p, tseq, 4);
       const uint32_t t_base = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
       const bool row_ok = row < p.M;
       const float bias_m = (p.bias_mode == 2 && row_ok) ? p.bias[row] : 0.f;
       const long long d_off = (long long)z * p.d_batch + (long long)row * p.ldd;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
+        const int col = col0 + c;
+        if (col >= p.N) break;              // uniform over the epilogue warps
+        if (p.debug_flags & 1) break;       // experiment: no epilogue work at all (output garbage)
         uint32_t v[32];
         tmem_ld32(t_base + c, v);
         tmem_ld_wait();
-        const int col = col0 + c;
-        if (col >= p.N) break;              // warp-uniform
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + bias_m;
@@ -183,50 +257,77 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __bfloat162float(__ldg(rp + i)) : 0.f;
           }
         }
-        if (row_ok) {
-          const bool full = (col + 32 <= p.N);
+        if (p.tma_store) {
+          // ---- staged path: this 128 x 32 sub-tile -> swizzled smem -> one TMA store
+          uint8_t* buf = cbuf + cb * GEMM_CSTAGE_BYTES;
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer cb's previous store has been read
+          epi_bar_sync();
+          uint8_t* rowp = buf + trow * row_bytes;
+          if (p.out_dtype == 2) {
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+              *reinterpret_cast<float4*>(rowp + ((ch ^ (trow & 7)) << 4)) = make_float4(f[4 * ch], f[4 * ch + 1], f[4 * ch + 2], f[4 * ch + 3]);
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              uint4 u;
+              if (p.out_dtype == 0) {
+                u = make_uint4(pack_h2(f[8 * ch], f[8 * ch + 1]), pack_h2(f[8 * ch + 2], f[8 * ch + 3]),
+                               pack_h2(f[8 * ch + 4], f[8 * ch + 5]), pack_h2(f[8 * ch + 6], f[8 * ch + 7]));
+              } else {
+                u = make_uint4(pack_bf2(f[8 * ch], f[8 * ch + 1]), pack_bf2(f[8 * ch + 2], f[8 * ch + 3]),
+                               pack_bf2(f[8 * ch + 4], f[8 * ch + 5]), pack_bf2(f[8 * ch + 6], f[8 * ch + 7]));
+              }
+              *reinterpret_cast<uint4*>(rowp + ((ch ^ ((trow >> 1) & 3)) << 4)) = u;
+            }
+          }
+          fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA (async proxy)
+          epi_bar_sync();
+          if (leader) {
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmD)),
+                         "r"(smem_u32(buf)), "r"(col), "r"(mt * GEMM_BLOCK_M), "r"(z)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          cb ^= 1;
+        } else if (row_ok) {
+          // ---- direct path (output pitch not TMA-compatible)
           if (p.out_dtype == 2) {
             float* d = reinterpret_cast<float*>(p.D) + d_off + col;
-            if (full && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(d + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-            } else {
-              for (int i = 0; i < 32; ++i)
-                if (col + i < p.N) d[i] = f[i];
-            }
+            for (int i = 0; i < 32; ++i)
+              if (col + i < p.N) d[i] = f[i];
           } else {
-            uint32_t h[16];
-            if (p.out_dtype == 0) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) h[i] = pack_h2(f[2 * i], f[2 * i + 1]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) h[i] = pack_bf2(f[2 * i], f[2 * i + 1]);
-            }
             uint16_t* d = reinterpret_cast<uint16_t*>(p.D) + d_off + col;
-            if (full && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4)
-                *reinterpret_cast<uint4*>(d + 2 * i) = make_uint4(h[i], h[i + 1], h[i + 2], h[i + 3]);
-            } else {
-              for (int i = 0; i < 32; ++i)
-                if (col + i < p.N) d[i] = (uint16_t)((i & 1) ? (h[i >> 1] >> 16) : (h[i >> 1] & 0xFFFF));
+            for (int i = 0; i < 32; ++i) {
+              if (col + i < p.N) {
+                if (p.out_dtype == 0) { const __half hv = __float2half_rn(f[i]); d[i] = *reinterpret_cast<const uint16_t*>(&hv); }
+                else { const __nv_bfloat16 bv = __float2bfloat16_rn(f[i]); d[i] = *reinterpret_cast<const uint16_t*>(&bv); }
+              }
             }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (leader) trace_stamp(p, tseq, 5);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&tempty_bar[acc]);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output bytes committed before exit
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();     // no CTA may exit while a peer can still multicast into it
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == 2) {
+    if (PAIR) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
 }
 
 }  // namespace pa

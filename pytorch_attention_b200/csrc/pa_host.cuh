@@ -99,7 +99,8 @@ inline int make_tmap_16b(CUtensorMap* out, int dtype, const void* base, int rank
     }
     if (box[i] == 0 || box[i] > 256) return fail(PA_ERR_BAD_SHAPE, "TMA box dim %d = %u out of range", i, box[i]);
   }
-  CUresult r = fn(out, dtype == PA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+  CUresult r = fn(out, dtype == PA_DTYPE_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                       : dtype == PA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                   (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swz == TM_SWZ_128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

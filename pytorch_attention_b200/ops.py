@@ -47,7 +47,7 @@ def workspace(nbytes, device):
     return buf
 
 
-def gemm_tn(a, b, bias=None, out=None, out_dtype=None, bias_mode=None, block_n=0, residual=None):
+def gemm_tn(a, b, bias=None, out=None, out_dtype=None, bias_mode=None, block_n=0, residual=None, cluster=0):
     """out[z][m,n] = sum_k a[z][m,k] b[z][n,k] (+bias).  a: [M,K] or [Z,M,K]; b: [N,K] or [Z,N,K] (row pitch may
     exceed K); bias fp32 per column (default) or per row (bias_mode=2)."""
     require_cuda(a, b, bias, out)
@@ -74,6 +74,7 @@ def gemm_tn(a, b, bias=None, out=None, out_dtype=None, bias_mode=None, block_n=0
     g.bias = _ptr(bias)
     g.bias_mode = 0 if bias is None else (bias_mode or 1)
     g.block_n = block_n
+    g.cluster = cluster
     if residual is not None:
         require_cuda(residual)
         assert residual.stride(-1) == 1 and residual.shape[-2:] == (M, N)

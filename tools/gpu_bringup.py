@@ -89,6 +89,32 @@ def probe_gemm():
              us=us, tflops=2.0 * M * N * K / us / 1e6)
 
 
+def probe_gemm_sweep():
+    """block_n x cluster sweep on the projection shapes of the BASELINE configs (correctness + time)."""
+    import torch
+    from pytorch_attention_b200 import ops
+    torch.manual_seed(0)
+    shapes = [(12608, 2304, 768), (12608, 768, 768), (12608, 3072, 1024), (131072, 512, 512), (401408, 1536, 512)]
+    for (M, N, K) in shapes:
+        A = torch.randn(M, K, device="cuda").half()
+        Bm = (torch.randn(N, K, device="cuda") / K ** 0.5).half()
+        ref = (A[:512].float() @ Bm.float().t())
+        for bn in (128, 192, 256):
+            for cl in (1, -2):
+                D = torch.empty(M, N, device="cuda", dtype=torch.float16)
+                try:
+                    ops.gemm_tn(A, Bm, out=D, block_n=bn, cluster=cl)
+                    torch.cuda.synchronize()
+                    err = (D[:512].float() - ref).abs().max().item()
+                    err2 = (D[-300:].float() - A[-300:].float() @ Bm.float().t()).abs().max().item()
+                    us = time_cuda(lambda: ops.gemm_tn(A, Bm, out=D, block_n=bn, cluster=cl), iters=10)
+                    emit(probe="gemm_sweep", M=M, N=N, K=K, bn=bn, cluster=cl, max_abs=max(err, err2), us=round(us, 2),
+                         tflops=round(2.0 * M * N * K / us / 1e6, 1))
+                except Exception as e:  # noqa: BLE001
+                    emit(probe="gemm_sweep", M=M, N=N, K=K, bn=bn, cluster=cl, error=str(e)[:200])
+        del A, Bm
+
+
 def probe_gemm_batched():
     import torch
     from pytorch_attention_b200 import ops
@@ -210,6 +236,7 @@ def probe_vit():
 PROBES = {
     "gemm_pattern": probe_gemm_pattern,
     "gemm": probe_gemm,
+    "gemm_sweep": probe_gemm_sweep,
     "gemm_batched": probe_gemm_batched,
     "attn_uniform": probe_attn_uniform,
     "attn": probe_attn,
