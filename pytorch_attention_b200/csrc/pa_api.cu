@@ -232,6 +232,7 @@ int attn_launch(const AttnLaunch& a, cudaStream_t st) {
   p.O = a.o; p.ldo = a.ldo; p.o_group = a.o_group; p.o_col0 = a.o_col0;
   p.scale_log2e = a.scale * 1.4426950408889634f;
   p.add_into_out = a.add_into_out;
+  p.trace = g_gemm_trace;
   CUtensorMap tq, tk, tv;
 
   if (!a.windowed) {

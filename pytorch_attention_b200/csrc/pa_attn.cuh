@@ -11,8 +11,9 @@
 // (a single block may be up to 256 wide): one block -> exact single-pass softmax; several blocks -> online
 // softmax with the running O rescaled in TMEM (cheap: HD columns per row).
 //
-// 384 threads:  warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM allocator |
-//               warps 4-7 softmax+epilogue of slot 0 | warps 8-11 of slot 1   (thread <-> query row <-> TMEM lane)
+// 320 threads:  warp 0 TMA producer (+ TMEM allocator) | warp 1 MMA issuer |
+//               warps 2-5 softmax+epilogue of slot 0 | warps 6-9 of slot 1   (thread <-> query row <-> TMEM lane;
+//               a warp may touch TMEM lanes 32*(warp%4)..+31, and any four consecutive warps cover all quarters)
 // TMEM slot (256 columns): S fp32 [0,kb)  ->  P fp16x2 [0,kb/2) written in place behind the S reads;
 //                          O fp32 [256-HD, 256) (aliases the tail of S only in the single-block case, where the
 //                          PV MMAs start after the softmax has drained S).
@@ -37,9 +38,12 @@ struct AttnParams {
   // windowed geometry (CSWin): image R x R, windows H_sp x W_sp, nJ windows per image row, nWin per image
   int R, H_sp, W_sp, nJ, nWin, h_box;
   int add_into_out;     // epilogue adds onto what O already holds (LePE)
+  long long* trace;     // debug: clock64 stamps of CTA 0 ([item][16]), or nullptr
 };
 
-constexpr int ATTN_THREADS = 384;
+#define ATTN_TRACE(seq, slot_) do { if (p.trace != nullptr && blockIdx.x == 0 && (seq) < 32) p.trace[(seq) * 16 + (slot_)] = clock64(); } while (0)
+
+constexpr int ATTN_THREADS = 320;   // 10 warps: more registers per softmax thread than 12 would leave (65536 / 320 = 204)
 constexpr int ATTN_SLOT_COLS = 256;
 
 template <int HD>
@@ -60,6 +64,50 @@ __host__ __device__ inline int attn_q_rows(bool windowed, int nkb, int kb_rows) 
 __host__ __device__ inline int attn_smem_bytes(int hd, bool windowed, int nkb, int kb, int kb_rows) {
   const int q_rows = windowed ? attn_q_rows(true, nkb, kb_rows) : 256;
   return 2 * q_rows * hd * 2 + 2 * 2 * kb * hd * 2 + 256 + 1024;
+}
+
+// ---- per-chunk softmax helpers (one thread = one query row; v = N consecutive S columns of that row)
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3
+  return r;
+}
+template <int N>
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[N], int nval, float mx) {
+  if (nval >= N) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) mx = max3f(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) mx = fmaxf(mx, (i < nval) ? __uint_as_float(v[i]) : -INFINITY);
+  }
+  return mx;
+}
+// p = exp2(s * sl2 - mxs) for the first nval columns (0 beyond), packed to fp16 pairs; returns the row-partial sum
+template <int N>
+__device__ __forceinline__ float chunk_exp(const uint32_t (&v)[N], uint32_t (&pk)[N / 2], int nval, float sl2, float mxs) {
+  float s0 = 0.f, s1 = 0.f;
+  if (nval >= N) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      const float e0 = ex2f(fmaf(__uint_as_float(v[i]), sl2, -mxs));
+      const float e1 = ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -mxs));
+      s0 += e0;
+      s1 += e1;
+      pk[i >> 1] = pack_h2(e0, e1);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      float e0 = 0.f, e1 = 0.f;
+      if (i < nval) e0 = ex2f(fmaf(__uint_as_float(v[i]), sl2, -mxs));          // nval is warp-uniform: no divergence,
+      if (i + 1 < nval) e1 = ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -mxs));  // and no MUFU work on padded keys
+      s0 += e0;
+      s1 += e1;
+      pk[i >> 1] = pack_h2(e0, e1);
+    }
+  }
+  return s0 + s1;
 }
 
 template <int HD, bool WINDOWED>
@@ -114,7 +162,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 0) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -174,70 +222,128 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp converged; one elected lane issues) =====================
+    // The two slots run half a period apart: per (item, key block) the issue order is
+    //     S(slot 0)  ->  PV(slot 1) of the PREVIOUS step  ->  S(slot 1)  ->  PV(slot 0)
+    // so one warpgroup is in its softmax (TMEM reads + MUFU) while the other waits on its MMA / writes its output,
+    // instead of both competing for the same TMEM lane-quarter ports and then idling together.
     int qb = 0, st = 0;
     uint32_t qph = 0, kph = 0;
     uint32_t se_ph0 = 0, se_ph1 = 0;     // slot_empty phase (one completion per item and slot)
     uint32_t pf_ph0 = 0, pf_ph1 = 0;     // p_full phase (one completion per block and slot)
     const int ksteps_o = p.kb / 16;
     const uint32_t q_base = smem_u32(q_smem), kv_base = smem_u32(kv_smem);
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    // pending PV of slot 1
+    bool pend = false;
+    uint32_t pend_kbuf = 0;
+    int pend_st = 0, pend_qb = 0, pend_acc = 0, pend_lastj = 0;
+    int iseq = 0;
+
+    auto issue_pv = [&](int s, uint32_t kbuf, int accumulate_blocks) {
+      const uint32_t slot = tmem_base + s * ATTN_SLOT_COLS;
+      // V block is [key][d] with d contiguous: MN-major B operand; 8-key groups are SBO bytes apart
+      const uint64_t vdesc = make_sdesc(kbuf + kvb_bytes, Cfg::SBO, Cfg::SBO, Cfg::SWZ);
+      for (int k = 0; k < ksteps_o; ++k)
+        umma_ts(slot + Cfg::O_COL, slot + 8 * k, vdesc + Cfg::V_KSTEP * k, p.idesc_o, (accumulate_blocks | k) != 0);
+      umma_commit(&o_full[s]);
+    };
+    auto flush_pending = [&]() {
+      if (!pend) return;
+      mbar_wait(&p_full[1], pf_ph1);
+      pf_ph1 ^= 1;
+      tc_fence_after();
+      if (elect_one()) {
+        issue_pv(1, pend_kbuf, pend_acc);
+        umma_commit(&kv_empty[pend_st]);            // slot 1's PV is the last reader of this K/V stage
+        if (pend_lastj) umma_commit(&q_empty[pend_qb]);
+      }
+      __syncwarp();
+      if (lane == 0) ATTN_TRACE(iseq, 4);
+      pend = false;
+    };
+
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++iseq) {
       const int pr = item % p.pairs;
       const int nslots = ((2 * pr + 1) < p.q_tiles) ? 2 : 1;
       const uint32_t qbuf = q_base + qb * q_bytes;
       mbar_wait(&q_full[qb], qph);
       tc_fence_after();
+      if (lane == 0) ATTN_TRACE(iseq, 0);
       for (int j = 0; j < p.nkb; ++j) {
         const uint32_t kbuf = kv_base + st * 2 * kvb_bytes;
         mbar_wait(&kv_full[st], kph);
         tc_fence_after();
         const uint64_t kdesc = make_sdesc(kbuf, 16, Cfg::SBO, Cfg::SWZ);
-        for (int s = 0; s < nslots; ++s) {
+        // ---- S of slot 0
+        {
           if (j == 0) {
-            mbar_wait(&slot_empty[s], (s ? se_ph1 : se_ph0) ^ 1);
-            if (s) se_ph1 ^= 1; else se_ph0 ^= 1;
+            mbar_wait(&slot_empty[0], se_ph0 ^ 1);
+            se_ph0 ^= 1;
             tc_fence_after();
           }
-          const int tile = WINDOWED ? (2 * pr + s) : s;
+          const int tile = WINDOWED ? (2 * pr) : 0;
           const uint64_t qdesc = make_sdesc(qbuf + tile * Cfg::Q_TILE_BYTES, 16, Cfg::SBO, Cfg::SWZ);
-          const uint32_t d = tmem_base + s * ATTN_SLOT_COLS;
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_ss(d, qdesc + 2 * k, kdesc + 2 * k, p.idesc_s, k != 0);
-            umma_commit(&s_full[s]);
+            for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_base, qdesc + 2 * k, kdesc + 2 * k, p.idesc_s, k != 0);
+            umma_commit(&s_full[0]);
           }
           __syncwarp();
+          if (lane == 0) ATTN_TRACE(iseq, 1);
         }
-        for (int s = 0; s < nslots; ++s) {
-          mbar_wait(&p_full[s], s ? pf_ph1 : pf_ph0);
-          if (s) pf_ph1 ^= 1; else pf_ph0 ^= 1;
-          tc_fence_after();
-          const uint32_t slot = tmem_base + s * ATTN_SLOT_COLS;
-          // V block is [key][d] with d contiguous: MN-major B operand; 8-key groups are SBO bytes apart
-          const uint64_t vdesc = make_sdesc(kbuf + kvb_bytes, Cfg::SBO, Cfg::SBO, Cfg::SWZ);
+        // ---- PV of slot 1 from the previous step
+        flush_pending();
+        // ---- S of slot 1
+        if (nslots == 2) {
+          if (j == 0) {
+            mbar_wait(&slot_empty[1], se_ph1 ^ 1);
+            se_ph1 ^= 1;
+            tc_fence_after();
+          }
+          const int tile = WINDOWED ? (2 * pr + 1) : 1;
+          const uint64_t qdesc = make_sdesc(qbuf + tile * Cfg::Q_TILE_BYTES, 16, Cfg::SBO, Cfg::SWZ);
           if (elect_one()) {
-            for (int k = 0; k < ksteps_o; ++k)
-              umma_ts(slot + Cfg::O_COL, slot + 8 * k, vdesc + Cfg::V_KSTEP * k, p.idesc_o, (j | k) != 0);
-            umma_commit(&o_full[s]);
-            if (s == nslots - 1) {
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k)
+              umma_ss(tmem_base + ATTN_SLOT_COLS, qdesc + 2 * k, kdesc + 2 * k, p.idesc_s, k != 0);
+            umma_commit(&s_full[1]);
+          }
+          __syncwarp();
+          if (lane == 0) ATTN_TRACE(iseq, 2);
+        }
+        // ---- PV of slot 0
+        {
+          mbar_wait(&p_full[0], pf_ph0);
+          pf_ph0 ^= 1;
+          tc_fence_after();
+          if (elect_one()) {
+            issue_pv(0, kbuf, j);
+            if (nslots == 1) {                       // no slot-1 work: slot 0's PV is the last reader
               umma_commit(&kv_empty[st]);
               if (j == p.nkb - 1) umma_commit(&q_empty[qb]);
             }
           }
           __syncwarp();
+          if (lane == 0) ATTN_TRACE(iseq, 3);
+        }
+        if (nslots == 2) {
+          pend = true; pend_kbuf = kbuf; pend_st = st; pend_qb = qb; pend_acc = j; pend_lastj = (j == p.nkb - 1);
         }
         if (++st == 2) { st = 0; kph ^= 1; }
       }
       if (++qb == 2) { qb = 0; qph ^= 1; }
     }
-  } else if (warp >= 4) {
-    // ===================== softmax + epilogue warpgroups =====================
-    const int slot = (warp - 4) >> 2;
+    flush_pending();
+  } else if (warp >= 2) {
+    // ===================== softmax + epilogue warpgroups (warps 2-5: slot 0, warps 6-9: slot 1) =====================
+    const int slot = (warp - 2) >> 2;
     const int q = warp & 3;
     const uint32_t t_slot = tmem_base + slot * ATTN_SLOT_COLS + ((uint32_t)(q * 32) << 16);
-    const int nchunks = (p.kb + 31) / 32;
     const float sl2 = p.scale_log2e;
     uint32_t sf_ph = 0, of_ph = 0;
+    int iseq = -1;
+    const bool tracer = (q == 0 && lane == 0);
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      ++iseq;
       const int pr = item % p.pairs;
       const int gh = item / p.pairs;
       const int h = gh % p.H, g = gh / p.H;
@@ -251,22 +357,36 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_wait(&s_full[slot], sf_ph);
         sf_ph ^= 1;
         tc_fence_after();
+        if (tracer && j == 0) ATTN_TRACE(iseq, 5 + 5 * slot);
         float alpha = 1.f, m_new = m_run;
         if (warp_active) {
-          // ---- pass 1: block row max
+          // ---- pass 1: block row max.  TMEM loads are software-pipelined: chunk c+1 is in flight while c is reduced.
           float mx = -INFINITY;
-          for (int c = 0; c < nchunks; ++c) {
-            uint32_t v[32];
-            tmem_ld32(t_slot + c * 32, v);
-            tmem_ld_wait();
-            if (c * 32 + 32 <= nvalid) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < nvalid) ? __uint_as_float(v[i]) : -INFINITY);
+          {
+            // few, wide TMEM loads: a tcgen05.ld costs ~150 cycles of latency whatever its width
+            int c = 0;
+#pragma unroll 1
+            for (; c + 64 <= p.kb; c += 64) {
+              uint32_t v[64];
+              tmem_ld64(t_slot + c, v);
+              tmem_ld_wait();
+              mx = chunk_max<64>(v, nvalid - c, mx);
+            }
+            if (c + 32 <= p.kb) {
+              uint32_t v[32];
+              tmem_ld32(t_slot + c, v);
+              tmem_ld_wait();
+              mx = chunk_max<32>(v, nvalid - c, mx);
+              c += 32;
+            }
+            if (c + 16 <= p.kb) {
+              uint32_t v[16];
+              tmem_ld16(t_slot + c, v);
+              tmem_ld_wait();
+              mx = chunk_max<16>(v, nvalid - c, mx);
             }
           }
+          if (tracer && j == 0) ATTN_TRACE(iseq, 6 + 5 * slot);
           m_new = fmaxf(m_run, mx);
           alpha = ex2f((m_run - m_new) * sl2);      // 0 on the first block (m_run = -inf)
         }
@@ -288,32 +408,27 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
         if (warp_active) {
-          // ---- pass 2: p = exp2((s - m) * scale*log2e), running sum, fp16 P in place
+          // ---- pass 2: p = exp2((s - m) * scale*log2e), running sum, fp16 P written in place behind the S reads
           const float mxs = m_new * sl2;
           float sum = 0.f;
-          for (int c = 0; c < nchunks; ++c) {
-            uint32_t v[32];
-            tmem_ld32(t_slot + c * 32, v);
-            tmem_ld_wait();
-            uint32_t pk[16];
-            if (c * 32 + 32 <= nvalid) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                const float e0 = ex2f(fmaf(__uint_as_float(v[i]), sl2, -mxs));
-                const float e1 = ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -mxs));
-                sum += e0 + e1;
-                pk[i >> 1] = pack_h2(e0, e1);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                const float e0 = (c * 32 + i < nvalid) ? ex2f(fmaf(__uint_as_float(v[i]), sl2, -mxs)) : 0.f;
-                const float e1 = (c * 32 + i + 1 < nvalid) ? ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -mxs)) : 0.f;
-                sum += e0 + e1;
-                pk[i >> 1] = pack_h2(e0, e1);
+          {
+            // 16-column steps, double buffered: step c+1 is in flight while step c goes through FFMA / MUFU.EX2 / pack
+            uint32_t va[16], vb[16], pk[8];
+            const int n16 = p.kb >> 4;
+            tmem_ld16(t_slot, va);
+#pragma unroll 1
+            for (int c = 0; c < n16; c += 2) {
+              tmem_ld_wait();
+              if (c + 1 < n16) tmem_ld16(t_slot + (c + 1) * 16, vb);
+              sum += chunk_exp<16>(va, pk, nvalid - c * 16, sl2, mxs);
+              tmem_st8(t_slot + c * 8, pk);
+              if (c + 1 < n16) {
+                tmem_ld_wait();
+                if (c + 2 < n16) tmem_ld16(t_slot + (c + 2) * 16, va);
+                sum += chunk_exp<16>(vb, pk, nvalid - (c + 1) * 16, sl2, mxs);
+                tmem_st8(t_slot + (c + 1) * 8, pk);
               }
             }
-            tmem_st16(t_slot + c * 16, pk);
           }
           tmem_st_wait();
           l_run = l_run * alpha + sum;
@@ -322,18 +437,24 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[slot]);
+        if (tracer && j == 0) ATTN_TRACE(iseq, 7 + 5 * slot);
       }
 
       // ---- epilogue: O / rowsum (+ LePE already in place) -> fp16 -> global
       mbar_wait(&o_full[slot], of_ph);
       of_ph ^= 1;
       tc_fence_after();
+      if (tracer) ATTN_TRACE(iseq, 8 + 5 * slot);
       if (warp_active) {
         const float inv = 1.f / l_run;
         uint32_t v[HD];
         tmem_ld32(t_slot + Cfg::O_COL, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
         if (HD == 64) tmem_ld32(t_slot + Cfg::O_COL + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[HD - 32]));
         tmem_ld_wait();
+        // O is in registers: hand the TMEM slot back NOW so the next S MMA overlaps the normalise + store below
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slot_empty[slot]);
         if (row < p.n_q) {
           long long tok;
           int grp;
@@ -367,16 +488,19 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&slot_empty[slot]);
+      if (!warp_active) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slot_empty[slot]);
+      }
+      if (tracer) ATTN_TRACE(iseq, 9 + 5 * slot);
     }
   }
 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace pa

@@ -50,3 +50,16 @@ def test_window_table_is_a_permutation(reso, idx, split):
 def test_window_table_bad_idx():
     with pytest.raises(ValueError):
         cswin_window_table(14, 2, 7)
+
+
+def test_aten_port_matches_oracle():
+    """The CPU baseline port (same ATen op sequence as the reference) agrees with the einsum oracle."""
+    from oracle import vit_attention
+    from oracle.aten_port import vit_attention_aten
+    torch.manual_seed(0)
+    x = torch.randn(2, 50, 128)
+    wq, bq = torch.randn(384, 128) * 0.1, torch.randn(384) * 0.1
+    wp, bp = torch.randn(128, 128) * 0.1, torch.randn(128) * 0.1
+    a = vit_attention(x, wq, bq, wp, bp, 2)
+    b = vit_attention_aten(x, wq, bq, wp, bp, 2)
+    assert (a - b).abs().max().item() < 1e-5
