@@ -199,8 +199,8 @@ struct AttnLaunch {
 };
 
 template <int HD, bool WIN>
-int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int smem,
-                  cudaStream_t st) {
+int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                  const AttnParams& p, int smem, cudaStream_t st) {
   static int attr_smem[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -209,7 +209,7 @@ int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
     attr_smem[dev & 63] = smem;
   }
   const int grid = p.items < num_sms() ? p.items : num_sms();
-  attn_core_kernel<HD, WIN><<<grid, ATTN_THREADS, smem, st>>>(tq, tk, tv, p);
+  attn_core_kernel<HD, WIN><<<grid, ATTN_THREADS, smem, st>>>(tq, tk, tv, to, p);
   PA_CUDA_OK(cudaGetLastError());
   launch_counter()++;
   return PA_OK;
@@ -288,8 +288,18 @@ int attn_launch(const AttnLaunch& a, cudaStream_t st) {
   p.idesc_o = make_idesc(128, hd, PA_F16, PA_F16, 0, 1);
   const int smem = attn_smem_bytes(hd, a.windowed, p.nkb, p.kb, p.kb_rows);
   if (smem > 227 * 1024) return fail(PA_ERR_UNSUPPORTED, "attention core: shared memory plan %d B too large", smem);
-  if (hd == 64) return a.windowed ? launch_attn_t<64, true>(tq, tk, tv, p, smem, st) : launch_attn_t<64, false>(tq, tk, tv, p, smem, st);
-  return a.windowed ? launch_attn_t<32, true>(tq, tk, tv, p, smem, st) : launch_attn_t<32, false>(tq, tk, tv, p, smem, st);
+  // output map for the staged TMA-store epilogue (non-windowed): {columns, rows of a group, groups}, box {hd, 128, 1}
+  CUtensorMap to = tq;
+  p.tma_store = 0;
+  if (!a.windowed && !getenv("PA_ATTN_DIRECT_STORE")) {
+    uint64_t dims[3] = {(uint64_t)a.ldo, (uint64_t)a.n_q, (uint64_t)a.G};
+    uint64_t str[2] = {(uint64_t)a.ldo * 2, (uint64_t)a.o_group * 2};
+    uint32_t box[3] = {(uint32_t)hd, 128, 1};
+    if ((rc = make_tmap_16b(&to, PA_DTYPE_F16, a.o, 3, dims, str, box, swz))) return rc;
+    p.tma_store = 1;
+  }
+  if (hd == 64) return a.windowed ? launch_attn_t<64, true>(tq, tk, tv, to, p, smem, st) : launch_attn_t<64, false>(tq, tk, tv, to, p, smem, st);
+  return a.windowed ? launch_attn_t<32, true>(tq, tk, tv, to, p, smem, st) : launch_attn_t<32, false>(tq, tk, tv, to, p, smem, st);
 }
 
 int attn_impl(const pa_attn_args* a, cudaStream_t st) {

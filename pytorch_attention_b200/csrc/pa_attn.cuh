@@ -39,6 +39,7 @@ struct AttnParams {
   int R, H_sp, W_sp, nJ, nWin, h_box;
   int add_into_out;     // epilogue adds onto what O already holds (LePE)
   long long* trace;     // debug: clock64 stamps of CTA 0 ([item][16]), or nullptr
+  int tma_store;        // non-windowed: output tile goes through smem + TMA store (tmO valid)
 };
 
 #define ATTN_TRACE(seq, slot_) do { if (p.trace != nullptr && blockIdx.x == 0 && (seq) < 32) p.trace[(seq) * 16 + (slot_)] = clock64(); } while (0)
@@ -61,9 +62,10 @@ __host__ __device__ inline int attn_q_rows(bool windowed, int nkb, int kb_rows) 
   const int r = windowed ? nkb * kb_rows : 256;
   return ((r < 512 ? 512 : r) + 7) / 8 * 8;      // windowed: last query tile may start at row 384 -> keep 512 rows mapped
 }
+__host__ __device__ inline int attn_ostage_bytes(int hd, bool windowed) { return windowed ? 0 : 2 * 128 * hd * 2; }
 __host__ __device__ inline int attn_smem_bytes(int hd, bool windowed, int nkb, int kb, int kb_rows) {
   const int q_rows = windowed ? attn_q_rows(true, nkb, kb_rows) : 256;
-  return 2 * q_rows * hd * 2 + 2 * 2 * kb * hd * 2 + 256 + 1024;
+  return 2 * q_rows * hd * 2 + 2 * 2 * kb * hd * 2 + attn_ostage_bytes(hd, windowed) + 256 + 1024;
 }
 
 // ---- per-chunk softmax helpers (one thread = one query row; v = N consecutive S columns of that row)
@@ -113,7 +115,7 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[N], uint32_t (&pk
 template <int HD, bool WINDOWED>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                  const AttnParams p) {
   using Cfg = AttnCfg<HD>;
   extern __shared__ uint8_t smem_raw[];
@@ -123,7 +125,8 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int kvb_bytes = p.kb * Cfg::ROW_BYTES;          // one K (or V) block buffer
   uint8_t* q_smem = smem;                               // [2][q_bytes]
   uint8_t* kv_smem = smem + 2 * q_bytes;                // [2 stages][K | V]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + 4 * kvb_bytes);
+  uint8_t* o_smem = kv_smem + 4 * kvb_bytes;            // [2 slots][128 rows x HD fp16] output staging (non-windowed)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(o_smem + attn_ostage_bytes(HD, WINDOWED));
   uint64_t* q_full = bars;            // [2] TMA -> MMA
   uint64_t* q_empty = bars + 2;       // [2] MMA -> TMA
   uint64_t* kv_full = bars + 4;       // [2]
@@ -455,7 +458,22 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&slot_empty[slot]);
-        if (row < p.n_q) {
+        if (!WINDOWED && p.tma_store) {
+          // ---- staged path: rows -> swizzled smem tile -> one TMA store per slot (clips rows >= n_q)
+          uint8_t* obuf = o_smem + slot * (128 * HD * 2);
+          const int trow = q * 32 + lane;
+          uint8_t* rowp = obuf + trow * (HD * 2);
+#pragma unroll
+          for (int i = 0; i < HD / 8; ++i) {
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[8 * i + k]) * inv;
+            const int sw = (HD == 64) ? (i ^ (trow & 7)) : (i ^ ((trow >> 1) & 3));     // SW128 / SW64 chunk swizzle
+            *reinterpret_cast<uint4*>(rowp + (sw << 4)) =
+                make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+          }
+          fence_proxy_async_smem();
+        } else if (row < p.n_q) {
           long long tok;
           int grp;
           if (WINDOWED) {
@@ -493,10 +511,24 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(&slot_empty[slot]);
       }
+      if (!WINDOWED && p.tma_store) {
+        // all four warps of the warpgroup (active or not) meet, then one thread issues the bulk store of the tile
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
+        if (q == 0 && lane == 0) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmO)),
+                       "r"(smem_u32(o_smem + slot * (128 * HD * 2))), "r"(p.o_col0 + h * HD), "r"(qt * 128), "r"(g)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile may be overwritten next item
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
+      }
       if (tracer) ATTN_TRACE(iseq, 9 + 5 * slot);
     }
   }
 
+  if (!WINDOWED && p.tma_store && warp >= 2 && (warp & 3) == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

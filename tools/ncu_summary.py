@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (raw page) and a launch-list CSV into profiles/*.md / traffic.json (run in the build container)."""
+import csv, io, json, subprocess, sys, collections
+
+WANT = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "lts__t_sector_hit_rate.pct", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed_pipe_xu.sum", "launch__grid_size", "launch__cluster_dim_x"]
+
+
+def raw_page(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    return hdr, units, rows[2:]
+
+
+def main(rep, launches_csv, tag):
+    hdr, units, rows = raw_page(rep)
+    ki = hdr.index("Kernel Name")
+    lines = [f"# ncu summary {tag}", "", f"source: `{rep}` (ncu --set full --clock-control none, one steady-state launch per kernel)", ""]
+    traffic = {}
+    for r in rows:
+        lines.append(f"## {r[ki][:90]}")
+        for w in WANT:
+            for i, h in enumerate(hdr):
+                if h == w:
+                    lines.append(f"- {w} = {r[i]} {units[i]}")
+        def val(name):
+            for i, h in enumerate(hdr):
+                if h == name:
+                    v = float(r[i].replace(",", ""))
+                    u = units[i].lower()
+                    return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+            return 0.0
+        tot = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+        lines.append(f"- dram bytes read+write per launch = {tot / 1e6:.2f} MB")
+        key = "attn" if "attn_core" in r[ki] else "gemm"
+        traffic.setdefault(key, []).append(tot)
+        lines.append("")
+    # launch list shares
+    rows2 = [r for r in csv.reader(open(launches_csv)) if len(r) > 10]
+    h2 = rows2[0]
+    k2, v2 = h2.index("Kernel Name"), h2.index("Metric Value")
+    agg = collections.defaultdict(list)
+    for r in rows2[1:]:
+        try:
+            agg[r[k2][:70]].append(float(r[v2].replace(",", "")))
+        except ValueError:
+            pass
+    tot = sum(sum(v) for v in agg.values())
+    lines += [f"## launch list ({launches_csv}; cold-cache, serialised: compare SHARES)", "", "| kernel | launches | mean us | share |", "|---|---|---|---|"]
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        lines.append(f"| `{k}` | {len(v)} | {sum(v) / len(v) / 1000:.2f} | {sum(v) / tot * 100:.1f}% |")
+    open(f"profiles/ncu_summary_{tag}.md", "w").write("\n".join(lines) + "\n")
+    gemm = traffic.get("gemm", [])
+    json.dump({"qkv_gemm_dram_bytes_per_launch": gemm[0] if gemm else None,
+               "attn_core_dram_bytes_per_launch": (traffic.get("attn") or [None])[0],
+               "source": f"profiles/ncu_summary_{tag}.md"}, open("profiles/traffic.json", "w"), indent=1)
+    print("\n".join(lines))
+
+
+if __name__ == "__main__":
+    main(*sys.argv[1:4])
