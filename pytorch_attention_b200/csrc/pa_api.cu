@@ -233,6 +233,7 @@ int attn_launch(const AttnLaunch& a, cudaStream_t st) {
   p.scale_log2e = a.scale * 1.4426950408889634f;
   p.add_into_out = a.add_into_out;
   p.trace = g_gemm_trace;
+  { const char* dbg = getenv("PA_ATTN_DEBUG"); p.debug_flags = dbg ? atoi(dbg) : 0; }
   CUtensorMap tq, tk, tv;
 
   if (!a.windowed) {

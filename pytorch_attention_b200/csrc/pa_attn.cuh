@@ -40,6 +40,7 @@ struct AttnParams {
   int add_into_out;     // epilogue adds onto what O already holds (LePE)
   long long* trace;     // debug: clock64 stamps of CTA 0 ([item][16]), or nullptr
   int tma_store;        // non-windowed: output tile goes through smem + TMA store (tmO valid)
+  int debug_flags;      // timing experiments only (env PA_ATTN_DEBUG): 1 = no MUFU in pass 2, 2 = no P store, 4 = skip pass 1
 };
 
 #define ATTN_TRACE(seq, slot_) do { if (p.trace != nullptr && blockIdx.x == 0 && (seq) < 32) p.trace[(seq) * 16 + (slot_)] = clock64(); } while (0)
@@ -110,6 +111,32 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[N], uint32_t (&pk
     }
   }
   return s0 + s1;
+}
+
+// Stage A of the skewed pass 2: e = exp2(s * sl2 - mxs) for the first nval columns of a 16-column step (0 beyond)
+__device__ __forceinline__ void exp_stage(const uint32_t (&v)[16], float (&e)[16], int nval, float sl2, float mxs, int dbg = 0) {
+  if (dbg & 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) e[i] = fmaf(__uint_as_float(v[i]), sl2, -mxs);
+  } else if (nval >= 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) e[i] = ex2f(fmaf(__uint_as_float(v[i]), sl2, -mxs));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      e[i] = 0.f;
+      if (i < nval) e[i] = ex2f(fmaf(__uint_as_float(v[i]), sl2, -mxs));   // nval is warp-uniform; padded keys never reach the MUFU
+    }
+  }
+}
+// Stage B: row-partial sum + fp16 pack of a step whose exponentials were issued one step earlier
+__device__ __forceinline__ void pack_stage(const float (&e)[16], uint32_t (&pk)[8], float& s0, float& s1) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    s0 += e[i];
+    s1 += e[i + 1];
+    pk[i >> 1] = pack_h2(e[i], e[i + 1]);
+  }
 }
 
 template <int HD, bool WINDOWED>
@@ -367,7 +394,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           float mx = -INFINITY;
           {
             // few, wide TMEM loads: a tcgen05.ld costs ~150 cycles of latency whatever its width
-            int c = 0;
+            int c = (p.debug_flags & 4) ? p.kb : 0;
 #pragma unroll 1
             for (; c + 64 <= p.kb; c += 64) {
               uint32_t v[64];
@@ -415,23 +442,36 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const float mxs = m_new * sl2;
           float sum = 0.f;
           {
-            // 16-column steps, double buffered: step c+1 is in flight while step c goes through FFMA / MUFU.EX2 / pack
+            // 16-column steps, skewed by one: the FFMA + MUFU.EX2 of step c+1 are issued BEFORE the sum / pack / tcgen05.st
+            // tail of step c, and the TMEM load of step c+2 is already in flight -> the MUFU pipe never waits on a tail.
             uint32_t va[16], vb[16], pk[8];
+            float ea[16], eb[16];
+            float s0 = 0.f, s1 = 0.f;
             const int n16 = p.kb >> 4;
             tmem_ld16(t_slot, va);
+            tmem_ld_wait();
+            if (n16 > 1) tmem_ld16(t_slot + 16, vb);
+            exp_stage(va, ea, nvalid, sl2, mxs, p.debug_flags);
 #pragma unroll 1
             for (int c = 0; c < n16; c += 2) {
-              tmem_ld_wait();
-              if (c + 1 < n16) tmem_ld16(t_slot + (c + 1) * 16, vb);
-              sum += chunk_exp<16>(va, pk, nvalid - c * 16, sl2, mxs);
-              tmem_st8(t_slot + c * 8, pk);
               if (c + 1 < n16) {
                 tmem_ld_wait();
                 if (c + 2 < n16) tmem_ld16(t_slot + (c + 2) * 16, va);
-                sum += chunk_exp<16>(vb, pk, nvalid - (c + 1) * 16, sl2, mxs);
-                tmem_st8(t_slot + (c + 1) * 8, pk);
+                exp_stage(vb, eb, nvalid - (c + 1) * 16, sl2, mxs, p.debug_flags);
+              }
+              pack_stage(ea, pk, s0, s1);
+              if (!(p.debug_flags & 2)) tmem_st8(t_slot + c * 8, pk);
+              if (c + 1 < n16) {
+                if (c + 2 < n16) {
+                  tmem_ld_wait();
+                  if (c + 3 < n16) tmem_ld16(t_slot + (c + 3) * 16, vb);
+                  exp_stage(va, ea, nvalid - (c + 2) * 16, sl2, mxs, p.debug_flags);
+                }
+                pack_stage(eb, pk, s0, s1);
+                if (!(p.debug_flags & 2)) tmem_st8(t_slot + (c + 1) * 8, pk);
               }
             }
+            sum = s0 + s1;
           }
           tmem_st_wait();
           l_run = l_run * alpha + sum;
