@@ -617,7 +617,13 @@ static int lepe_run(const pa_cswin_lepe_args* a, cudaStream_t st) {
   lp.B = a->B; lp.R = a->resolution; lp.Cb = a->C; lp.H_sp = Hs; lp.W_sp = Ws;
   if (a->batch_stride != (long long)a->L * a->ld || a->out_batch_stride != (long long)a->L * a->ldo)
     return fail(PA_ERR_UNSUPPORTED, "pa_cswin_lepe: batch pitch must equal L * row pitch");
-  lepe_kernel<<<grid_for((long long)a->B * a->L * (a->C / 8), 256), 256, 0, st>>>(lp);
+  const int lepe_smem = (LEPE_RB + 2) * a->resolution * 128;
+  if (a->C % 64 == 0 && lepe_smem <= 48 * 1024) {
+    const int nblk = a->B * ((a->resolution + LEPE_RB - 1) / LEPE_RB) * (a->C / 64);
+    lepe_tiled_kernel<<<nblk, 256, lepe_smem, st>>>(lp);
+  } else {
+    lepe_kernel<<<grid_for((long long)a->B * a->L * (a->C / 8), 256), 256, 0, st>>>(lp);
+  }
   PA_CUDA_OK(cudaGetLastError());
   launch_counter()++;
   // ... then the windowed attention adds softmax(q k^T scale) v on top (cswin.py:116-121) and scatters to image order (122-125)

@@ -54,7 +54,8 @@ struct GemmCfg {
   static constexpr int B_BYTES = B_ROWS * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int C_OFFSET = STAGES * STAGE_BYTES;             // 2 output staging buffers
-  static constexpr int BAR_OFFSET = C_OFFSET + 2 * GEMM_CSTAGE_BYTES;
+  static constexpr int BIAS_OFFSET = C_OFFSET + 2 * GEMM_CSTAGE_BYTES;   // BLOCK_N fp32 column biases of the current tile
+  static constexpr int BAR_OFFSET = BIAS_OFFSET + 1024;
   static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;        // + barriers + 1024-alignment slack
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
@@ -226,6 +227,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = row < p.M;
       const float bias_m = (p.bias_mode == 2 && row_ok) ? p.bias[row] : 0.f;
       const long long d_off = (long long)z * p.d_batch + (long long)row * p.ldd;
+      float* sbias = reinterpret_cast<float*>(smem + Cfg::BIAS_OFFSET);
+      if (p.bias_mode == 1) {
+        // column biases of this tile: one coalesced load into smem, then broadcast reads (was 32 scalar LDGs per chunk)
+        const int et = threadIdx.x - 128;
+        for (int i = et; i < BLOCK_N; i += 128) sbias[i] = (col0 + i < p.N) ? __ldg(p.bias + col0 + i) : 0.f;
+        epi_bar_sync();
+      }
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
         const int col = col0 + c;
@@ -239,7 +247,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + bias_m;
         if (p.bias_mode == 1) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __ldg(p.bias + col + i) : 0.f;
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + i);
+            f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+          }
         }
         if (p.residual != nullptr && row_ok) {
           const long long r_off = (long long)z * p.r_batch + (long long)row * p.ldr + col;
@@ -247,14 +258,31 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float* rp = reinterpret_cast<const float*>(p.residual) + r_off;
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __ldg(rp + i) : 0.f;
-          } else if (p.res_dtype == 0) {
-            const __half* rp = reinterpret_cast<const __half*>(p.residual) + r_off;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __half2float(__ldg(rp + i)) : 0.f;
           } else {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off;
+            const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + r_off;
+            if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __bfloat162float(__ldg(rp + i)) : 0.f;
+              for (int i = 0; i < 4; ++i) {               // 4 x 16-byte loads of this row's 32 residual values
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (p.res_dtype == 0) {
+                    const __half2 h = *reinterpret_cast<const __half2*>(&w[k]);
+                    f[8 * i + 2 * k] += __low2float(h); f[8 * i + 2 * k + 1] += __high2float(h);
+                  } else {
+                    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+                    f[8 * i + 2 * k] += __low2float(h); f[8 * i + 2 * k + 1] += __high2float(h);
+                  }
+                }
+              }
+            } else if (p.res_dtype == 0) {
+              const __half* hp = reinterpret_cast<const __half*>(rp);
+              for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __half2float(__ldg(hp + i)) : 0.f;
+            } else {
+              const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(rp);
+              for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __bfloat162float(__ldg(bp + i)) : 0.f;
+            }
           }
         }
         if (p.tma_store) {
@@ -291,23 +319,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           cb ^= 1;
-        } else if (row_ok) {
-          // ---- direct path (output pitch not TMA-compatible)
-          if (p.out_dtype == 2) {
-            float* d = reinterpret_cast<float*>(p.D) + d_off + col;
-            for (int i = 0; i < 32; ++i)
-              if (col + i < p.N) d[i] = f[i];
-          } else {
-            uint16_t* d = reinterpret_cast<uint16_t*>(p.D) + d_off + col;
-            for (int i = 0; i < 32; ++i) {
-              if (col + i < p.N) {
-                if (p.out_dtype == 0) { const __half hv = __float2half_rn(f[i]); d[i] = *reinterpret_cast<const uint16_t*>(&hv); }
-                else { const __nv_bfloat16 bv = __float2bfloat16_rn(f[i]); d[i] = *reinterpret_cast<const uint16_t*>(&bv); }
-              }
+        } else {
+          // ---- unaligned output pitch (e.g. CvT's NCHW rows of 196): stage the warp's 32 x 32 block in smem (padded rows),
+          //      then each warp instruction writes ONE row's 32 contiguous elements (coalesced) instead of 32 scattered ones
+          float* wbuf = reinterpret_cast<float*>(cbuf) + q * (32 * 33);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) wbuf[lane * 33 + i] = f[i];
+          __syncwarp();
+          const int row0 = mt * GEMM_BLOCK_M + q * 32;
+          for (int r = 0; r < 32; ++r) {
+            if (row0 + r >= p.M) break;
+            if (col + lane < p.N) {
+              const float val = wbuf[r * 33 + lane];
+              const long long off = (long long)z * p.d_batch + (long long)(row0 + r) * p.ldd + col + lane;
+              if (p.out_dtype == 2) reinterpret_cast<float*>(p.D)[off] = val;
+              else if (p.out_dtype == 0) reinterpret_cast<__half*>(p.D)[off] = __float2half_rn(val);
+              else reinterpret_cast<__nv_bfloat16*>(p.D)[off] = __float2bfloat16_rn(val);
             }
           }
         }
       }
+      if (p.bias_mode == 1 && !p.tma_store) epi_bar_sync();   // nobody may refill the bias buffer while it is being read
       tc_fence_before();
       __syncwarp();
       if (leader) trace_stamp(p, tseq, 5);

@@ -132,10 +132,56 @@ struct LnParams {
   long long rows; int C, dtype; float eps;
 };
 __global__ void layernorm_kernel(const LnParams p) {
+  // one warp per row; the row is read ONCE into registers (up to 4 x 8 elements per lane = C <= 1024), longer rows
+  // fall back to re-reading.  Statistics in fp32, two-pass (mean, then centred variance) like ATen's layer_norm.
   const int lane = threadIdx.x & 31;
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (row >= p.rows) return;
   const uint16_t* xr = reinterpret_cast<const uint16_t*>(p.x) + row * p.C;
+  uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + row * p.C;
+  if (p.C <= 1024) {
+    float f[4][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (j * 32 + lane) * 8;
+      if (c < p.C) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xr + c)), p.dtype, f[j]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += f[j][k];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / p.C;
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (j * 32 + lane) * 8;
+      if (c < p.C) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v = fmaf(f[j][k] - mean, f[j][k] - mean, v);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v / p.C + p.eps);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (j * 32 + lane) * 8;
+      if (c < p.C) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + c + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + c + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o8[k] = fmaf((f[j][k] - mean) * rstd, gg[k], bb[k]);
+        *reinterpret_cast<uint4*>(orow + c) = pack8(o8, 0);
+      }
+    }
+    return;
+  }
   float s = 0.f;
   for (int c = lane * 8; c < p.C; c += 256) {
     float f[8];
@@ -161,7 +207,7 @@ __global__ void layernorm_kernel(const LnParams p) {
     unpack8(__ldg(reinterpret_cast<const uint4*>(xr + c)), p.dtype, f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o8[k] = fmaf((f[k] - mean) * rstd, __ldg(p.gamma + c + k), __ldg(p.beta + c + k));
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + row * p.C + c) = pack8(o8, 0);
+    *reinterpret_cast<uint4*>(orow + c) = pack8(o8, 0);
   }
 }
 
@@ -365,6 +411,64 @@ __global__ void lepe_kernel(const LepeParams p) {
     }
     const long long tok = (long long)b * p.R * p.R + (long long)row * p.R + col;
     *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + tok * p.ldo + p.o_col0 + c0) = pack8(acc, 0);
+  }
+}
+
+// Tiled variant: a block owns LEPE_RB image rows x 64 channels of one image; the RB+2 input rows are staged in shared
+// memory once (each V element comes from L2 (RB+2)/RB times instead of 9 times), window borders are applied on the fly.
+constexpr int LEPE_RB = 4;
+__global__ void __launch_bounds__(256) lepe_tiled_kernel(const LepeParams p) {
+  extern __shared__ uint4 lepe_smem[];                 // [(RB+2) rows][R tokens][8 x 16 B]
+  const int R = p.R;
+  const int cchunks = p.Cb / 64;
+  const int cc = blockIdx.x % cchunks;
+  const int rb = (blockIdx.x / cchunks) % ((R + LEPE_RB - 1) / LEPE_RB);
+  const int b = blockIdx.x / (cchunks * ((R + LEPE_RB - 1) / LEPE_RB));
+  const int row0 = rb * LEPE_RB;
+  const int c0 = cc * 64;
+  const int nrows = LEPE_RB + 2;
+  for (int i = threadIdx.x; i < nrows * R * 8; i += 256) {
+    const int cv = i & 7;
+    const int col = (i >> 3) % R;
+    const int rr = (i >> 3) / R;
+    const int row = row0 + rr - 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (row >= 0 && row < R) {
+      const long long tok = (long long)b * R * R + (long long)row * R + col;
+      val = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.v) + tok * p.ldv + p.v_col0 + c0 + cv * 8));
+    }
+    lepe_smem[i] = val;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < LEPE_RB * R * 8; i += 256) {
+    const int cv = i & 7;
+    const int col = (i >> 3) % R;
+    const int rr = (i >> 3) / R;
+    const int row = row0 + rr;
+    if (row >= R) continue;
+    const int r_in = row % p.H_sp, c_in = col % p.W_sp;
+    const int ch = c0 + cv * 8;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = __ldg(p.bias + ch + k);
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      if (r_in + u - 1 < 0 || r_in + u - 1 >= p.H_sp) continue;
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        if (c_in + v - 1 < 0 || c_in + v - 1 >= p.W_sp) continue;
+        float xf[8];
+        unpack8(lepe_smem[((rr + u) * R + (col + v - 1)) * 8 + cv], 0, xf);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + (u * 3 + v) * p.Cb + ch));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + (u * 3 + v) * p.Cb + ch + 4));
+        acc[0] = fmaf(xf[0], w0.x, acc[0]); acc[1] = fmaf(xf[1], w0.y, acc[1]);
+        acc[2] = fmaf(xf[2], w0.z, acc[2]); acc[3] = fmaf(xf[3], w0.w, acc[3]);
+        acc[4] = fmaf(xf[4], w1.x, acc[4]); acc[5] = fmaf(xf[5], w1.y, acc[5]);
+        acc[6] = fmaf(xf[6], w1.z, acc[6]); acc[7] = fmaf(xf[7], w1.w, acc[7]);
+      }
+    }
+    const long long tok = (long long)b * R * R + (long long)row * R + col;
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + tok * p.ldo + p.o_col0 + ch) = pack8(acc, 0);
   }
 }
 

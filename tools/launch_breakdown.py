@@ -1,0 +1,18 @@
+"""One forward of each non-headline config (for an ncu launch list: which kernel costs what)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import pytorch_attention_b200 as pa
+torch.manual_seed(0)
+dev = "cuda"
+def go(mod, x, call):
+    mod = mod.eval().half().cuda()
+    with torch.no_grad():
+        for _ in range(2):
+            call(mod, x)
+    torch.cuda.synchronize()
+go(pa.pvt.Attention(512, 8, sr_ratio=8), torch.randn(32, 4096, 512, device=dev).half(), lambda m, x: m(x, 64, 64))
+go(pa.cswin.CSWinBlock(512, 56, 16, split_size=7, qkv_bias=True), torch.randn(128, 3136, 512, device=dev).half(), lambda m, x: m.attention_half(x))
+go(pa.xcit.XCA(768, 12), torch.randn(64, 196, 768, device=dev).half(), lambda m, x: m(x))
+go(pa.cvt.Attention(384, 6), torch.randn(64, 384, 14, 14, device=dev).half(), lambda m, x: m(x))
+go(pa.xcit.ClassAttention(768, 12), torch.randn(64, 197, 768, device=dev).half(), lambda m, x: m(x))
