@@ -287,12 +287,15 @@ int attn_launch(const AttnLaunch& a, cudaStream_t st) {
   p.items = p.G * p.H * p.pairs;
   p.idesc_s = make_idesc(128, p.kb, PA_F16, PA_F16, 0, 0);
   p.idesc_o = make_idesc(128, hd, PA_F16, PA_F16, 0, 1);
-  const int smem = attn_smem_bytes(hd, a.windowed, p.nkb, p.kb, p.kb_rows);
+  // staged TMA-store epilogue when the plan still fits (and rows are consecutive tokens), else direct stores
+  bool staged = !a.windowed && !getenv("PA_ATTN_DIRECT_STORE") &&
+                attn_smem_bytes(hd, false, p.nkb, p.kb, p.kb_rows, true) <= 227 * 1024;
+  const int smem = attn_smem_bytes(hd, a.windowed, p.nkb, p.kb, p.kb_rows, staged);
   if (smem > 227 * 1024) return fail(PA_ERR_UNSUPPORTED, "attention core: shared memory plan %d B too large", smem);
   // output map for the staged TMA-store epilogue (non-windowed): {columns, rows of a group, groups}, box {hd, 128, 1}
   CUtensorMap to = tq;
   p.tma_store = 0;
-  if (!a.windowed && !getenv("PA_ATTN_DIRECT_STORE")) {
+  if (staged) {
     uint64_t dims[3] = {(uint64_t)a.ldo, (uint64_t)a.n_q, (uint64_t)a.G};
     uint64_t str[2] = {(uint64_t)a.ldo * 2, (uint64_t)a.o_group * 2};
     uint32_t box[3] = {(uint32_t)hd, 128, 1};

@@ -11,9 +11,12 @@
 // (a single block may be up to 256 wide): one block -> exact single-pass softmax; several blocks -> online
 // softmax with the running O rescaled in TMEM (cheap: HD columns per row).
 //
-// 320 threads:  warp 0 TMA producer (+ TMEM allocator) | warp 1 MMA issuer |
-//               warps 2-5 softmax+epilogue of slot 0 | warps 6-9 of slot 1   (thread <-> query row <-> TMEM lane;
-//               a warp may touch TMEM lanes 32*(warp%4)..+31, and any four consecutive warps cover all quarters)
+// 576 threads:  warp 0 TMA producer (+ TMEM allocator) | warp 1 MMA issuer |
+//               warps 2-9 softmax+epilogue of slot 0 | warps 10-17 of slot 1.  TWO threads per query row (a warp may
+//               touch TMEM lanes 32*(warp%4)..+31, so warps w and w+4 of a slot share a lane quarter): each owns one
+//               half of the row's S columns end to end -- partial max (exchanged through smem), exponentials, its half
+//               of P written IN PLACE inside its own S columns, partial row sum, its half of the O columns.
+//               Four softmax warps per scheduler instead of two: a single warp cannot keep the MUFU busy (measured).
 // TMEM slot (256 columns): S fp32 [0,kb)  ->  P fp16x2 [0,kb/2) written in place behind the S reads;
 //                          O fp32 [256-HD, 256) (aliases the tail of S only in the single-block case, where the
 //                          PV MMAs start after the softmax has drained S).
@@ -45,7 +48,8 @@ struct AttnParams {
 
 #define ATTN_TRACE(seq, slot_) do { if (p.trace != nullptr && blockIdx.x == 0 && (seq) < 32) p.trace[(seq) * 16 + (slot_)] = clock64(); } while (0)
 
-constexpr int ATTN_THREADS = 320;   // 10 warps: more registers per softmax thread than 12 would leave (65536 / 320 = 204)
+constexpr int ATTN_THREADS = 640;   // 2 control warps + 2 slots x 8 softmax warps (two threads per query row) + 2 idle:
+                                    // registers are allocated to warps in groups of four, so 18 warps cost as much as 20
 constexpr int ATTN_SLOT_COLS = 256;
 
 template <int HD>
@@ -63,10 +67,10 @@ __host__ __device__ inline int attn_q_rows(bool windowed, int nkb, int kb_rows) 
   const int r = windowed ? nkb * kb_rows : 256;
   return ((r < 512 ? 512 : r) + 7) / 8 * 8;      // windowed: last query tile may start at row 384 -> keep 512 rows mapped
 }
-__host__ __device__ inline int attn_ostage_bytes(int hd, bool windowed) { return windowed ? 0 : 2 * 128 * hd * 2; }
-__host__ __device__ inline int attn_smem_bytes(int hd, bool windowed, int nkb, int kb, int kb_rows) {
+__host__ __device__ inline int attn_ostage_bytes(int hd, bool staged) { return (staged ? 2 * 128 * hd * 2 : 0) + 4096; }   // + max/sum exchange
+__host__ __device__ inline int attn_smem_bytes(int hd, bool windowed, int nkb, int kb, int kb_rows, bool staged) {
   const int q_rows = windowed ? attn_q_rows(true, nkb, kb_rows) : 256;
-  return 2 * q_rows * hd * 2 + 2 * 2 * kb * hd * 2 + attn_ostage_bytes(hd, windowed) + 256 + 1024;
+  return 2 * q_rows * hd * 2 + 2 * 2 * kb * hd * 2 + attn_ostage_bytes(hd, staged) + 256 + 1024;
 }
 
 // ---- per-chunk softmax helpers (one thread = one query row; v = N consecutive S columns of that row)
@@ -153,7 +157,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* q_smem = smem;                               // [2][q_bytes]
   uint8_t* kv_smem = smem + 2 * q_bytes;                // [2 stages][K | V]
   uint8_t* o_smem = kv_smem + 4 * kvb_bytes;            // [2 slots][128 rows x HD fp16] output staging (non-windowed)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(o_smem + attn_ostage_bytes(HD, WINDOWED));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(o_smem + attn_ostage_bytes(HD, p.tma_store != 0));
   uint64_t* q_full = bars;            // [2] TMA -> MMA
   uint64_t* q_empty = bars + 2;       // [2] MMA -> TMA
   uint64_t* kv_full = bars + 4;       // [2]
@@ -186,9 +190,9 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[i], 8);
       mbar_init(&o_full[i], 1);
-      mbar_init(&slot_empty[i], 4);
+      mbar_init(&slot_empty[i], 8);
     }
     fence_mbar_init();
   }
@@ -261,6 +265,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint32_t se_ph0 = 0, se_ph1 = 0;     // slot_empty phase (one completion per item and slot)
     uint32_t pf_ph0 = 0, pf_ph1 = 0;     // p_full phase (one completion per block and slot)
     const int ksteps_o = p.kb / 16;
+    const int h16 = (ksteps_o + 1) / 2;         // 16-column steps owned by the first thread of each row
     const uint32_t q_base = smem_u32(q_smem), kv_base = smem_u32(kv_smem);
     // pending PV of slot 1
     bool pend = false;
@@ -272,8 +277,11 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t slot = tmem_base + s * ATTN_SLOT_COLS;
       // V block is [key][d] with d contiguous: MN-major B operand; 8-key groups are SBO bytes apart
       const uint64_t vdesc = make_sdesc(kbuf + kvb_bytes, Cfg::SBO, Cfg::SBO, Cfg::SWZ);
-      for (int k = 0; k < ksteps_o; ++k)
-        umma_ts(slot + Cfg::O_COL, slot + 8 * k, vdesc + Cfg::V_KSTEP * k, p.idesc_o, (accumulate_blocks | k) != 0);
+      // P of keys [0, 16*h16) sits at columns 8k; P of the second half of the keys sits inside ITS thread's S columns
+      for (int k = 0; k < ksteps_o; ++k) {
+        const int pcol = (k < h16) ? 8 * k : 16 * h16 + 8 * (k - h16);
+        umma_ts(slot + Cfg::O_COL, slot + pcol, vdesc + Cfg::V_KSTEP * k, p.idesc_o, (accumulate_blocks | k) != 0);
+      }
       umma_commit(&o_full[s]);
     };
     auto flush_pending = [&]() {
@@ -363,63 +371,62 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (++qb == 2) { qb = 0; qph ^= 1; }
     }
     flush_pending();
-  } else if (warp >= 2) {
-    // ===================== softmax + epilogue warpgroups (warps 2-5: slot 0, warps 6-9: slot 1) =====================
-    const int slot = (warp - 2) >> 2;
-    const int q = warp & 3;
+  } else if (warp >= 2 && warp < 18) {
+    // ===================== softmax + epilogue: 8 warps per slot, two threads per query row =====================
+    const int sw = warp - 2;
+    const int slot = sw >> 3;
+    const int hf = (sw >> 2) & 1;             // which half of the row's columns this thread owns
+    const int q = warp & 3;                   // TMEM lane quarter of this warp
+    const int trow = q * 32 + lane;           // row inside the 128-row tile
     const uint32_t t_slot = tmem_base + slot * ATTN_SLOT_COLS + ((uint32_t)(q * 32) << 16);
+    const int n16 = p.kb >> 4;
+    const int h16 = (n16 + 1) / 2;
+    const int c_lo = hf ? h16 * 16 : 0;       // first S column of this thread
+    const int nst = hf ? n16 - h16 : h16;     // its number of 16-column steps
+    const uint32_t t_my = t_slot + c_lo;      // its S columns; its P goes in place at t_my + 8k
     const float sl2 = p.scale_log2e;
+    float* xch = reinterpret_cast<float*>(o_smem + attn_ostage_bytes(HD, p.tma_store != 0) - 4096);
+    float* xmax = xch + (slot * 2) * 128;     // [2 halves][128 rows]
+    float* xsum = xch + 512 + (slot * 2) * 128;
+    constexpr int OH = HD / 2;                // O columns per thread
+    const uint32_t t_o = t_slot + Cfg::O_COL + hf * OH;
     uint32_t sf_ph = 0, of_ph = 0;
     int iseq = -1;
-    const bool tracer = (q == 0 && lane == 0);
+    const bool tracer = (q == 0 && hf == 0 && lane == 0);
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       ++iseq;
       const int pr = item % p.pairs;
       const int gh = item / p.pairs;
       const int h = gh % p.H, g = gh / p.H;
       const int qt = 2 * pr + slot;
-      if (qt >= p.q_tiles) continue;          // slot idle for this item (uniform over the warpgroup)
-      const int row = qt * 128 + q * 32 + lane;
+      if (qt >= p.q_tiles) continue;          // slot idle for this item (uniform over the slot's warps)
+      const int row = qt * 128 + trow;
       const bool warp_active = (qt * 128 + q * 32) < p.n_q;
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < p.nkb; ++j) {
-        const int nvalid = min(p.kb_rows, p.n_k - j * p.kb_rows);    // real keys in this block
+        const int nvalid = min(p.kb_rows, p.n_k - j * p.kb_rows) - c_lo;    // real keys among this thread's columns
         mbar_wait(&s_full[slot], sf_ph);
         sf_ph ^= 1;
         tc_fence_after();
         if (tracer && j == 0) ATTN_TRACE(iseq, 5 + 5 * slot);
-        float alpha = 1.f, m_new = m_run;
+        // ---- pass 1: partial row max over this thread's columns
+        float mx = -INFINITY;
         if (warp_active) {
-          // ---- pass 1: block row max.  TMEM loads are software-pipelined: chunk c+1 is in flight while c is reduced.
-          float mx = -INFINITY;
-          {
-            // few, wide TMEM loads: a tcgen05.ld costs ~150 cycles of latency whatever its width
-            int c = (p.debug_flags & 4) ? p.kb : 0;
+          int k = (p.debug_flags & 4) ? nst : 0;
 #pragma unroll 1
-            for (; c + 64 <= p.kb; c += 64) {
-              uint32_t v[64];
-              tmem_ld64(t_slot + c, v);
-              tmem_ld_wait();
-              mx = chunk_max<64>(v, nvalid - c, mx);
-            }
-            if (c + 32 <= p.kb) {
-              uint32_t v[32];
-              tmem_ld32(t_slot + c, v);
-              tmem_ld_wait();
-              mx = chunk_max<32>(v, nvalid - c, mx);
-              c += 32;
-            }
-            if (c + 16 <= p.kb) {
-              uint32_t v[16];
-              tmem_ld16(t_slot + c, v);
-              tmem_ld_wait();
-              mx = chunk_max<16>(v, nvalid - c, mx);
-            }
+          for (; k < nst; ++k) {
+            uint32_t v[16];
+            tmem_ld16(t_my + k * 16, v);
+            tmem_ld_wait();
+            mx = chunk_max<16>(v, nvalid - k * 16, mx);
           }
-          if (tracer && j == 0) ATTN_TRACE(iseq, 6 + 5 * slot);
-          m_new = fmaxf(m_run, mx);
-          alpha = ex2f((m_run - m_new) * sl2);      // 0 on the first block (m_run = -inf)
         }
+        xmax[hf * 128 + trow] = mx;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");
+        mx = fmaxf(mx, xmax[(hf ^ 1) * 128 + trow]);
+        if (tracer && j == 0) ATTN_TRACE(iseq, 6 + 5 * slot);
+        const float m_new = fmaxf(m_run, mx);
+        const float alpha = ex2f((m_run - m_new) * sl2);      // 0 on the first block (m_run = -inf)
         if (j > 0) {
           // previous block's PV must have retired before O is rescaled / P overwritten
           mbar_wait(&o_full[slot], of_ph);
@@ -427,89 +434,74 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc_fence_after();
           if (warp_active) {
 #pragma unroll
-            for (int c = 0; c < HD; c += 16) {
+            for (int c = 0; c < OH; c += 16) {
               uint32_t o[16];
-              tmem_ld16(t_slot + AttnCfg<HD>::O_COL + c, o);
+              tmem_ld16(t_o + c, o);
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st16(t_slot + AttnCfg<HD>::O_COL + c, o);
+              tmem_st16(t_o + c, o);
             }
           }
         }
         if (warp_active) {
-          // ---- pass 2: p = exp2((s - m) * scale*log2e), running sum, fp16 P written in place behind the S reads
+          // ---- pass 2: p = exp2((s - m) * scale*log2e) over this thread's columns; fp16 P in place; partial row sum
           const float mxs = m_new * sl2;
-          float sum = 0.f;
-          {
-            // 16-column steps, skewed by one: the FFMA + MUFU.EX2 of step c+1 are issued BEFORE the sum / pack / tcgen05.st
-            // tail of step c, and the TMEM load of step c+2 is already in flight -> the MUFU pipe never waits on a tail.
-            uint32_t va[16], vb[16], pk[8];
-            float ea[16], eb[16];
-            float s0 = 0.f, s1 = 0.f;
-            const int n16 = p.kb >> 4;
-            tmem_ld16(t_slot, va);
-            tmem_ld_wait();
-            if (n16 > 1) tmem_ld16(t_slot + 16, vb);
-            exp_stage(va, ea, nvalid, sl2, mxs, p.debug_flags);
+          uint32_t va[16], pk[8];
+          float e[16];
+          float s0 = 0.f, s1 = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < n16; c += 2) {
-              if (c + 1 < n16) {
-                tmem_ld_wait();
-                if (c + 2 < n16) tmem_ld16(t_slot + (c + 2) * 16, va);
-                exp_stage(vb, eb, nvalid - (c + 1) * 16, sl2, mxs, p.debug_flags);
-              }
-              pack_stage(ea, pk, s0, s1);
-              if (!(p.debug_flags & 2)) tmem_st8(t_slot + c * 8, pk);
-              if (c + 1 < n16) {
-                if (c + 2 < n16) {
-                  tmem_ld_wait();
-                  if (c + 3 < n16) tmem_ld16(t_slot + (c + 3) * 16, vb);
-                  exp_stage(va, ea, nvalid - (c + 2) * 16, sl2, mxs, p.debug_flags);
-                }
-                pack_stage(eb, pk, s0, s1);
-                if (!(p.debug_flags & 2)) tmem_st8(t_slot + (c + 1) * 8, pk);
-              }
-            }
-            sum = s0 + s1;
+          for (int k = 0; k < nst; ++k) {      // four softmax warps per scheduler hide the TMEM / MUFU latencies of each other
+            tmem_ld16(t_my + k * 16, va);
+            tmem_ld_wait();
+            exp_stage(va, e, nvalid - k * 16, sl2, mxs, p.debug_flags);
+            pack_stage(e, pk, s0, s1);
+            tmem_st8(t_my + k * 8, pk);
           }
           tmem_st_wait();
-          l_run = l_run * alpha + sum;
+          l_run = l_run * alpha + (s0 + s1);
           m_run = m_new;
         }
+        if (j == p.nkb - 1) xsum[hf * 128 + trow] = l_run;     // partial row sum for the partner (ordered by p_full -> o_full)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[slot]);
         if (tracer && j == 0) ATTN_TRACE(iseq, 7 + 5 * slot);
       }
 
-      // ---- epilogue: O / rowsum (+ LePE already in place) -> fp16 -> global
+      // ---- epilogue: this thread's half of the O columns / rowsum (+ LePE already in place) -> fp16 -> global
       mbar_wait(&o_full[slot], of_ph);
       of_ph ^= 1;
       tc_fence_after();
       if (tracer) ATTN_TRACE(iseq, 8 + 5 * slot);
+      uint32_t v[OH];
       if (warp_active) {
-        const float inv = 1.f / l_run;
-        uint32_t v[HD];
-        tmem_ld32(t_slot + Cfg::O_COL, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        if (HD == 64) tmem_ld32(t_slot + Cfg::O_COL + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[HD - 32]));
+        if (OH == 32) tmem_ld32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        else tmem_ld16(t_o, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
         tmem_ld_wait();
-        // O is in registers: hand the TMEM slot back NOW so the next S MMA overlaps the normalise + store below
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&slot_empty[slot]);
+      }
+      // O is in registers: hand the TMEM slot back NOW so the next S MMA overlaps the normalise + store below
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_empty[slot]);
+      if (!WINDOWED && p.tma_store) {
+        // the staging tile is free once the PREVIOUS item's bulk store has read it (long ago: off the critical path)
+        if (sw == slot * 8 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");
+      }
+      if (warp_active) {
+        const float inv = 1.f / (l_run + xsum[(hf ^ 1) * 128 + trow]);
         if (!WINDOWED && p.tma_store) {
           // ---- staged path: rows -> swizzled smem tile -> one TMA store per slot (clips rows >= n_q)
-          uint8_t* obuf = o_smem + slot * (128 * HD * 2);
-          const int trow = q * 32 + lane;
-          uint8_t* rowp = obuf + trow * (HD * 2);
+          uint8_t* rowp = o_smem + slot * (128 * HD * 2) + trow * (HD * 2);
 #pragma unroll
-          for (int i = 0; i < HD / 8; ++i) {
+          for (int i = 0; i < OH / 8; ++i) {
             float f[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[8 * i + k]) * inv;
-            const int sw = (HD == 64) ? (i ^ (trow & 7)) : (i ^ ((trow >> 1) & 3));     // SW128 / SW64 chunk swizzle
-            *reinterpret_cast<uint4*>(rowp + (sw << 4)) =
+            const int ch = hf * (OH / 8) + i;                                              // 16-byte chunk of the row
+            const int swz = (HD == 64) ? (ch ^ (trow & 7)) : (ch ^ ((trow >> 1) & 3));     // SW128 / SW64 chunk swizzle
+            *reinterpret_cast<uint4*>(rowp + (swz << 4)) =
                 make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
           }
           fence_proxy_async_smem();
@@ -526,10 +518,10 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tok = row;
             grp = g;
           }
-          uint16_t* dst = reinterpret_cast<uint16_t*>(p.O) + (long long)grp * p.o_group + tok * p.ldo + p.o_col0 + h * HD;
+          uint16_t* dst = reinterpret_cast<uint16_t*>(p.O) + (long long)grp * p.o_group + tok * p.ldo + p.o_col0 + h * HD + hf * OH;
           uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-          for (int i = 0; i < HD / 8; ++i) {
+          for (int i = 0; i < OH / 8; ++i) {
             float f[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[8 * i + k]) * inv;
@@ -546,29 +538,22 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
       }
-      if (!warp_active) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&slot_empty[slot]);
-      }
       if (!WINDOWED && p.tma_store) {
-        // all four warps of the warpgroup (active or not) meet, then one thread issues the bulk store of the tile
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
-        if (q == 0 && lane == 0) {
+        // all eight warps of the slot (active or not) meet, then one thread issues the bulk store of the tile
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");
+        if (sw == slot * 8 && lane == 0) {
           asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                            reinterpret_cast<uint64_t>(&tmO)),
                        "r"(smem_u32(o_smem + slot * (128 * HD * 2))), "r"(p.o_col0 + h * HD), "r"(qt * 128), "r"(g)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile may be overwritten next item
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
       }
       if (tracer) ATTN_TRACE(iseq, 9 + 5 * slot);
     }
   }
 
-  if (!WINDOWED && p.tma_store && warp >= 2 && (warp & 3) == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (!WINDOWED && p.tma_store && (warp == 2 || warp == 10) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
