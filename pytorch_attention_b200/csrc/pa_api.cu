@@ -37,6 +37,7 @@ int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     attr_done[dev & 63] = true;
   }
   p.m_groups = (p.m_tiles + CL - 1) / CL;
+  if (!(PAIR && BN == 256)) p.balanced = 0;
   const int supertiles = p.m_groups * p.n_tiles * p.Z;
   const int max_clusters = num_sms() / CL;
   const int nclusters = supertiles < max_clusters ? supertiles : max_clusters;
@@ -115,10 +116,14 @@ int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
 
   int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, a->K, a->Z);
   int cl = a->cluster ? a->cluster : pick_cluster((a->M + 127) / 128);
+  if (!a->block_n && cl == -2 && getenv("PA_GEMM_BALANCED")) bn = 256;   // experimental: balanced unit walk needs 256-wide tiles
   if (cl != 1 && cl != 2 && cl != 4 && cl != -2) return fail(PA_ERR_UNSUPPORTED, "pa_gemm_tn: cluster %d not in {1,2,4,-2}", cl);
   if (bn == 96 && cl == 4) cl = 2;          // B slices must stay whole 8-row swizzle atoms
   const bool pair = (cl == -2);             // cta_group::2: CTA pairs, 256-row tiles, each CTA stages half of B
-  const int b_box_rows = pair ? bn / 2 : bn / cl;
+  // balanced unit partition (32-row B boxes): measured 2 % better than the classic order at BLOCK_N 256 but worse than
+  // classic BLOCK_N 192 on the ViT shapes (four small TMA boxes per k-block, less A-tile sharing in L2) -> opt-in only
+  const bool balanced = pair && bn == 256 && getenv("PA_GEMM_BALANCED");
+  const int b_box_rows = balanced ? 32 : pair ? bn / 2 : bn / cl;
   CUtensorMap tmA, tmB;
   {
     const int za = a->a_batch ? a->Z : 1;
@@ -147,6 +152,8 @@ int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
   p.residual = a->residual; p.ldr = a->ldr; p.r_batch = a->r_batch; p.res_dtype = a->res_dtype;
   p.idesc = make_idesc(pair ? 256 : 128, bn, a->a_dtype, a->b_dtype, 0, 0);
   p.trace = g_gemm_trace;
+  p.balanced = balanced ? 1 : 0;
+  p.n_units = (a->N + 63) / 64;
   { const char* dbg = getenv("PA_GEMM_DEBUG"); p.debug_flags = dbg ? atoi(dbg) : 0; }
   // output map for the staged TMA-store epilogue (128 x 32 sub-tiles); needs 16-byte aligned base and pitches
   const int elt = a->out_dtype == PA_DTYPE_F32 ? 4 : 2;

@@ -31,6 +31,8 @@ struct GemmParams {
   long long ldr, r_batch;
   int res_dtype;
   int tma_store;           // 1: epilogue goes through smem + TMA store (tmD valid)
+  int balanced;            // PAIR + BLOCK_N 256 only: balanced contiguous partition of 64-column units (see TileWalk)
+  int n_units;             // ceil(N / 64)
   uint32_t idesc;
   long long* trace;        // debug: per-tile clock64 stamps of CTA 0 ([tile][8]), or nullptr
   int debug_flags;         // debug experiments (env PA_GEMM_DEBUG): 1 = skip epilogue body
@@ -63,6 +65,47 @@ struct GemmCfg {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// Tile sequence of one persistent worker (a CTA, or a cluster).  Classic: tiles `first, first+stride, ...` of fixed width.
+// Balanced: the (m-group, 64-column unit) grid is cut into equal contiguous ranges, one per worker, and each range is walked
+// as tiles of up to four units inside one m-group -- no partially filled last wave (e.g. 450 tiles on 74 pairs = 6.08 waves
+// cost 7 rounds in the classic order, 6.08 here).  All three roles of a CTA walk the same sequence.
+struct TileWalk {
+  long long cur, end;      // balanced: unit range; classic: tile index / count
+  int stride, per_z, n_cols_units, block_n, balanced;
+  int z, mg, col0, ncols;
+  __device__ TileWalk(const GemmParams& p, int worker, int nworkers, int block_n_) {
+    balanced = p.balanced; block_n = block_n_;
+    if (balanced) {
+      n_cols_units = p.n_units;
+      per_z = p.m_groups * p.n_units;
+      const long long total = (long long)per_z * p.Z;
+      cur = total * worker / nworkers;
+      end = total * (worker + 1) / nworkers;
+      stride = 0;
+    } else {
+      n_cols_units = p.n_tiles;
+      per_z = p.m_groups * p.n_tiles;
+      cur = worker; end = (long long)per_z * p.Z; stride = nworkers;
+    }
+  }
+  __device__ bool next() {
+    if (cur >= end) return false;
+    z = (int)(cur / per_z);
+    const int r = (int)(cur - (long long)z * per_z);
+    mg = r / n_cols_units;
+    const int u = r - mg * n_cols_units;
+    if (balanced) {
+      int w = n_cols_units - u;
+      if (w > 4) w = 4;
+      if (w > end - cur) w = (int)(end - cur);
+      col0 = u * 64; ncols = w * 64; cur += w;
+    } else {
+      col0 = u * block_n; ncols = block_n; cur += stride;
+    }
+    return true;
+  }
+};
+
 // CLUSTER > 1: the CTAs of a cluster take adjacent m-tiles of the same n-tile; each loads 1/CLUSTER of the B tile and
 // TMA-multicasts it to all of them (L2->SM traffic per flop drops from (128+BN) to (128+BN/CLUSTER) rows per k-block).
 // A stage may be refilled only after EVERY CTA's MMAs have read it: the consumer release is a multicast commit.
@@ -91,8 +134,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
-  const int tiles_per_z = p.m_groups * p.n_tiles;        // super-tiles (CLUSTER m-tiles x 1 n-tile) per batch
-  const int num_tiles = tiles_per_z * p.Z;
   const int crank = (CLUSTER > 1) ? (int)cluster_ctarank() : 0;
   const int cid = blockIdx.x / CLUSTER;                  // cluster index = persistent worker index
   const int ncl = gridDim.x / CLUSTER;
@@ -130,11 +171,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int stage = 0, tseq = 0;
     uint32_t phase = 0;
     if (lane == 0) trace_stamp(p, 0, 0);
-    for (int tile = cid; tile < num_tiles; tile += ncl, ++tseq) {
-      const int z = tile / tiles_per_z;
-      const int r = tile - z * tiles_per_z;
-      const int mg = r / p.n_tiles, nt = r - mg * p.n_tiles;
-      const int mt = mg * CLUSTER + crank;
+    TileWalk tw(p, cid, ncl, BLOCK_N);
+    for (; tw.next(); ++tseq) {
+      const int z = tw.z;
+      const int mt = tw.mg * CLUSTER + crank;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -142,16 +182,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one()) {
           if (kb == 0) trace_stamp(p, tseq, 6);
           if (PAIR) {
-            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            const int b_rows = tw.ncols / 2;               // rows of B this CTA stages (half of the tile's columns)
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + b_rows * 128));
             tma_load_3d_2sm(sa, &tmA, kb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M, p.a_batched ? z : 0, &full_bar[stage]);
-            tma_load_3d_2sm(sb, &tmB, kb * GEMM_BLOCK_K, nt * BLOCK_N + crank * Cfg::B_ROWS, p.b_batched ? z : 0, &full_bar[stage]);
+            if (p.balanced) {                              // B map has 32-row boxes: one per 64-column unit of the tile
+              for (int i = 0; i < b_rows; i += 32)
+                tma_load_3d_2sm(sb + i * 128, &tmB, kb * GEMM_BLOCK_K, tw.col0 + crank * b_rows + i, p.b_batched ? z : 0, &full_bar[stage]);
+            } else {
+              tma_load_3d_2sm(sb, &tmB, kb * GEMM_BLOCK_K, tw.col0 + crank * Cfg::B_ROWS, p.b_batched ? z : 0, &full_bar[stage]);
+            }
           } else {
             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             tma_load_3d(sa, &tmA, kb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M, p.a_batched ? z : 0, &full_bar[stage]);
             if (CLUSTER == 1) {
-              tma_load_3d(sb, &tmB, kb * GEMM_BLOCK_K, nt * BLOCK_N, p.b_batched ? z : 0, &full_bar[stage]);
+              tma_load_3d(sb, &tmB, kb * GEMM_BLOCK_K, tw.col0, p.b_batched ? z : 0, &full_bar[stage]);
             } else {
-              tma_load_3d_mc(sb + crank * B_SLICE_ROWS * 128, &tmB, kb * GEMM_BLOCK_K, nt * BLOCK_N + crank * B_SLICE_ROWS,
+              tma_load_3d_mc(sb + crank * B_SLICE_ROWS * 128, &tmB, kb * GEMM_BLOCK_K, tw.col0 + crank * B_SLICE_ROWS,
                              p.b_batched ? z : 0, &full_bar[stage], CMASK);
             }
           }
@@ -168,11 +214,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t smem_base = smem_u32(smem);
-      for (int tile = cid; tile < num_tiles; tile += ncl, ++tseq) {
+      TileWalk tw(p, cid, ncl, BLOCK_N);
+      for (; tw.next(); ++tseq) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         if (lane == 0) trace_stamp(p, tseq, 1);
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t idesc = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)(tw.ncols >> 3) << 17);   // MMA N = width of this tile
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -184,8 +232,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
               // advance 16 elements (32 bytes) along K inside the 128B swizzle atom: +2 in 16-byte units
-              if (PAIR) umma_ss2(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) != 0);
-              else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) != 0);
+              if (PAIR) umma_ss2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
             }
             // frees the smem stage (in every CTA that multicasts into it / is read by the pair MMA) when these MMAs retire
             if (PAIR) umma_commit2_mc(&empty_bar[stage], CMASK);
@@ -213,13 +261,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* cbuf = smem + Cfg::C_OFFSET;
     int acc = 0, cb = 0, tseq = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cid; tile < num_tiles; tile += ncl, ++tseq) {
-      const int z = tile / tiles_per_z;
-      const int r = tile - z * tiles_per_z;
-      const int mg = r / p.n_tiles, nt = r - mg * p.n_tiles;
-      const int mt = mg * CLUSTER + crank;
+    TileWalk tw(p, cid, ncl, BLOCK_N);
+    for (; tw.next(); ++tseq) {
+      const int z = tw.z;
+      const int mt = tw.mg * CLUSTER + crank;
       const int row = mt * GEMM_BLOCK_M + trow;
-      const int col0 = nt * BLOCK_N;
+      const int col0 = tw.col0;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (leader) trace_stamp(p, tseq, 4);
@@ -231,11 +278,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.bias_mode == 1) {
         // column biases of this tile: one coalesced load into smem, then broadcast reads (was 32 scalar LDGs per chunk)
         const int et = threadIdx.x - 128;
-        for (int i = et; i < BLOCK_N; i += 128) sbias[i] = (col0 + i < p.N) ? __ldg(p.bias + col0 + i) : 0.f;
+        for (int i = et; i < tw.ncols; i += 128) sbias[i] = (col0 + i < p.N) ? __ldg(p.bias + col0 + i) : 0.f;
         epi_bar_sync();
       }
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+      for (int c = 0; c < tw.ncols; c += 32) {
         const int col = col0 + c;
         if (col >= p.N) break;              // uniform over the epilogue warps
         if (p.debug_flags & 1) break;       // experiment: no epilogue work at all (output garbage)
