@@ -108,6 +108,13 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, int
       : "memory");
 }
 
+// L2 prefetch of a box (no smem destination, no barrier): warms the next tile's operands while the current one computes
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // multicast variant: the box lands at the same smem offset in every CTA of `cta_mask`, and each destination CTA's
 // mbarrier (same offset) receives the complete_tx for the bytes written there.
 __device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar,

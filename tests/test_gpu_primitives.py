@@ -88,3 +88,55 @@ def test_attn_uniform_when_keys_are_zero():
     qkv[0, :, 2 * C:] = V
     o = ops.attn_core(qkv, qkv, 1, 0.125, 0, C, 2 * C)
     assert torch.equal(o[0].float(), V.float().mean(0, keepdim=True).expand(N, -1).half().float())
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, -2])
+@pytest.mark.parametrize("bn", [128, 256])
+def test_gemm_cluster_modes_bit_exact(cluster, bn):
+    """Every scheduling mode of the GEMM (single CTA, TMA-multicast clusters of 2 / 4, cta_group::2 pairs) must give
+    the same bits on integer-valued operands (index path: multicast slices, peer-CTA halves of B, remote barriers)."""
+    ops = _ops()
+    torch.manual_seed(7)
+    M, N, K = 1000, 520, 192
+    A = torch.randint(-3, 4, (M, K), device="cuda").half()
+    B = torch.randint(-3, 4, (N, K), device="cuda").half()
+    D = ops.gemm_tn(A, B, out_dtype=torch.float32, block_n=bn, cluster=cluster)
+    assert torch.equal(D, A.float() @ B.float().t())
+
+
+@pytest.mark.parametrize("res_dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_gemm_residual_and_bias(res_dtype):
+    ops = _ops()
+    torch.manual_seed(8)
+    M, N, K = 700, 512, 256
+    A = torch.randn(M, K, device="cuda").half()
+    B = (torch.randn(N, K, device="cuda") / 16).half()
+    bias = torch.randn(N, device="cuda")
+    R = torch.randn(M, N, device="cuda").to(res_dtype)
+    D = ops.gemm_tn(A, B, bias=bias, residual=R, out_dtype=torch.float32)
+    ref = A.float() @ B.float().t() + bias + R.float()
+    assert (D - ref).abs().max().item() <= 3e-5 * ref.abs().max().item()
+
+
+def test_gemm_unaligned_output_pitch():
+    """Output rows of 196 fp16 (392 B, not 16-byte aligned: CvT's NCHW maps) take the smem-staged fallback store."""
+    ops = _ops()
+    torch.manual_seed(9)
+    Z, M, N, K = 2, 192, 196, 128
+    W = torch.randint(-3, 4, (M, K), device="cuda").half()
+    O = torch.randint(-3, 4, (Z, N, K), device="cuda").half()
+    D = ops.gemm_tn(W, O, out_dtype=torch.float16)
+    assert D.stride(1) == 196
+    assert torch.equal(D.float(), torch.einsum("mk,znk->zmn", W.float(), O.float()))
+
+
+def test_gemm_balanced_walk_env(monkeypatch):
+    """Opt-in balanced 64-column-unit tile walk (variable-width tiles, 32-row B boxes) is bit-exact too."""
+    ops = _ops()
+    monkeypatch.setenv("PA_GEMM_BALANCED", "1")
+    torch.manual_seed(10)
+    M, N, K = 3000, 840, 320
+    A = torch.randint(-3, 4, (M, K), device="cuda").half()
+    B = torch.randint(-3, 4, (N, K), device="cuda").half()
+    D = ops.gemm_tn(A, B, out_dtype=torch.float32)
+    assert torch.equal(D, A.float() @ B.float().t())
