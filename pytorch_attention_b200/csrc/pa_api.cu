@@ -78,27 +78,29 @@ int pick_cluster(int m_tiles) {
   return m_tiles >= 2 ? -2 : 1;
 }
 
-int pick_block_n(int M, int N, int K, int Z) {
+int pick_block_n(int M, int N, int K, int Z, bool pair) {
   const char* env = getenv("PA_GEMM_BN");
   if (env) {
     int v = atoi(env);
     if (v == 64 || v == 96 || v == 128 || v == 192 || v == 256) return v;
   }
   const int cands[5] = {256, 192, 128, 96, 64};
-  const int sms = num_sms();
-  const int m_tiles = (M + 127) / 128;
+  // workers: CTA pairs working on 256-row tiles, or single CTAs on 128-row tiles
+  const int workers = pair ? num_sms() / 2 : num_sms();
+  const int m_tiles = pair ? (M + 255) / 256 : (M + 127) / 128;
   const int num_kb = (K + 63) / 64;
   double best = 1e30;
   int best_bn = 128;
   for (int i = 0; i < 5; ++i) {
     const int bn = cands[i];
     const long long tiles = (long long)m_tiles * ((N + bn - 1) / bn) * Z;
-    const long long waves = (tiles + sms - 1) / sms;
-    // MMA cycles per tile + fixed per-tile overhead; narrow tiles pay extra L2 traffic per flop
+    const long long waves = (tiles + workers - 1) / workers;
+    // MMA cycles per tile (the tensor core walks N in 64-column steps of 32 cycles) + fixed per-tile overhead;
+    // narrow tiles pay more shared-memory traffic per flop
     double per_tile = 2.0 * num_kb * bn + 700.0;
     if (bn < 128) per_tile *= 1.0 + 0.10 * (128.0 / bn - 1.0);
-    const double cost = waves * per_tile;
-    if (cost < best) { best = cost; best_bn = bn; }
+    const double cost = waves * per_tile + 0.5 * per_tile;     // + the exposed epilogue of the last tile
+    if (cost < best * 0.999) { best = cost; best_bn = bn; }
   }
   return best_bn;
 }
@@ -114,8 +116,8 @@ int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
   int rc = current_device_check();
   if (rc) return rc;
 
-  int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, a->K, a->Z);
   int cl = a->cluster ? a->cluster : pick_cluster((a->M + 127) / 128);
+  int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, a->K, a->Z, cl == -2);
   if (!a->block_n && cl == -2 && getenv("PA_GEMM_BALANCED")) bn = 256;   // experimental: balanced unit walk needs 256-wide tiles
   if (cl != 1 && cl != 2 && cl != 4 && cl != -2) return fail(PA_ERR_UNSUPPORTED, "pa_gemm_tn: cluster %d not in {1,2,4,-2}", cl);
   if (bn == 96 && cl == 4) cl = 2;          // B slices must stay whole 8-row swizzle atoms
