@@ -253,7 +253,7 @@ def run_ours(args, rank, world, local):
         sampler.stop_flag = True
         sampler.join()
         barrier(world)
-        launches = (_lib.launch_count() - l0) if not graphs else 3 * args.steps
+        launches = (_lib.launch_count() - l0) if not graphs else (1 if args.fused else 3) * args.steps
         elapsed_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
 
         # ---- end-to-end leg: host (pinned) x -> H2D -> forward -> D2H y, every step, copies inside the timed region
@@ -357,7 +357,7 @@ def run_ours(args, rank, world, local):
                     global_batch=B * world, per_gpu_batch=B, tokens_per_step=tokens, io_dtype=args.dtype, out_dtype="fp16",
                     accumulate="fp32", parallelism=f"dp{world} (batch-sharded, no collective)",
                     l2="inputs/outputs rotate over a ring of %d buffers (%.0f MB) > 126 MB L2" % (RING, RING * 2 * B * N * C * 2 / 1e6),
-                    cuda_graph=not args.no_graph),
+                    cuda_graph=not args.no_graph, fused_single_launch=bool(args.fused)),
         step_tflops=flops_step * world / (ms_per_step * 1e-3) / 1e12,
         step_frac_of_peak=flops_step / (ms_per_step * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
         roofline=dict(bound="tensor", kernel="gemm_tn_kernel (qkv projection)", achieved=achieved, peak=roof_peak, unit="TFLOP/s",
@@ -381,7 +381,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="opt-in single-launch fused kernel (PA_VIT_FUSED=1)")
     args = ap.parse_args()
+    if args.fused:
+        os.environ["PA_VIT_FUSED"] = "1"
     rank, world, local = dist_setup(args.gpus)
     try:
         if args.impl == "reference":

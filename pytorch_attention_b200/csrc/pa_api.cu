@@ -1,6 +1,7 @@
 // pa_api.cu — C-ABI entry points of libpa_b200.so (see include/pa_b200.h).
 #include "pa_attn.cuh"
 #include "pa_gemm.cuh"
+#include "pa_fused.cuh"
 #include "pa_host.cuh"
 #include "pa_misc.cuh"
 
@@ -105,7 +106,16 @@ int pick_block_n(int M, int N, int K, int Z, bool pair) {
   return best_bn;
 }
 
-int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
+struct GemmPlan {
+  CUtensorMap tmA, tmB, tmD;
+  GemmParams p;
+  int bn, cl;
+};
+
+// validates, picks the tile configuration (or takes force_bn / force_cl), builds tensor maps and kernel parameters
+int gemm_prepare(const pa_gemm_args* a, GemmPlan* plan, int force_bn = 0, int force_cl = 0) {
+  CUtensorMap& tmA = plan->tmA; CUtensorMap& tmB = plan->tmB; CUtensorMap& tmD = plan->tmD;
+  GemmParams& p = plan->p;
   if (!a) return fail(PA_ERR_NULL, "pa_gemm_tn: args is NULL");
   if (!a->A || !a->B || !a->D) return fail(PA_ERR_NULL, "pa_gemm_tn: A/B/D must be non-NULL");
   if (a->M <= 0 || a->N <= 0 || a->K <= 0 || a->Z <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_gemm_tn: M,N,K,Z must be positive");
@@ -116,8 +126,8 @@ int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
   int rc = current_device_check();
   if (rc) return rc;
 
-  int cl = a->cluster ? a->cluster : pick_cluster((a->M + 127) / 128);
-  int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, a->K, a->Z, cl == -2);
+  int cl = force_cl ? force_cl : a->cluster ? a->cluster : pick_cluster((a->M + 127) / 128);
+  int bn = force_bn ? force_bn : a->block_n ? a->block_n : pick_block_n(a->M, a->N, a->K, a->Z, cl == -2);
   if (!a->block_n && cl == -2 && getenv("PA_GEMM_BALANCED")) bn = 256;   // experimental: balanced unit walk needs 256-wide tiles
   if (cl != 1 && cl != 2 && cl != 4 && cl != -2) return fail(PA_ERR_UNSUPPORTED, "pa_gemm_tn: cluster %d not in {1,2,4,-2}", cl);
   if (bn == 96 && cl == 4) cl = 2;          // B slices must stay whole 8-row swizzle atoms
@@ -126,7 +136,6 @@ int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
   // classic BLOCK_N 192 on the ViT shapes (four small TMA boxes per k-block, less A-tile sharing in L2) -> opt-in only
   const bool balanced = pair && bn == 256 && getenv("PA_GEMM_BALANCED");
   const int b_box_rows = balanced ? 32 : pair ? bn / 2 : bn / cl;
-  CUtensorMap tmA, tmB;
   {
     const int za = a->a_batch ? a->Z : 1;
     uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->M, (uint64_t)za};
@@ -143,7 +152,6 @@ int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
     rc = make_tmap_16b(&tmB, a->b_dtype, a->B, 3, dims, str, box);
     if (rc) return rc;
   }
-  GemmParams p;
   p.M = a->M; p.N = a->N; p.K = a->K; p.Z = a->Z;
   p.m_tiles = (a->M + 127) / 128;
   p.n_tiles = (a->N + bn - 1) / bn;
@@ -155,13 +163,14 @@ int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
   p.idesc = make_idesc(pair ? 256 : 128, bn, a->a_dtype, a->b_dtype, 0, 0);
   p.trace = g_gemm_trace;
   p.balanced = balanced ? 1 : 0;
+  p.wait_ctr = nullptr; p.wait_rows = 1; p.wait_target = 0; p.signal_ctr = nullptr; p.reverse_workers = 0;
   p.n_units = (a->N + 63) / 64;
   { const char* dbg = getenv("PA_GEMM_DEBUG"); p.debug_flags = dbg ? atoi(dbg) : 0; }
   // output map for the staged TMA-store epilogue (128 x 32 sub-tiles); needs 16-byte aligned base and pitches
   const int elt = a->out_dtype == PA_DTYPE_F32 ? 4 : 2;
   p.tma_store = ((reinterpret_cast<uintptr_t>(a->D) & 15) == 0) && ((a->ldd * elt) % 16 == 0) &&
                 (a->Z == 1 || (a->d_batch * elt) % 16 == 0) && !getenv("PA_GEMM_DIRECT_STORE");
-  CUtensorMap tmD = tmA;
+  tmD = tmA;
   if (p.tma_store) {
     uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->Z};
     uint64_t str[2] = {(uint64_t)a->ldd * elt, (uint64_t)(a->Z > 1 ? a->d_batch : a->ldd * (long long)a->M) * elt};
@@ -169,6 +178,17 @@ int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
     rc = make_tmap_16b(&tmD, a->out_dtype, a->D, 3, dims, str, box, elt == 4 ? TM_SWZ_128 : TM_SWZ_64);
     if (rc) return rc;
   }
+  plan->bn = bn; plan->cl = cl;
+  return PA_OK;
+}
+
+int gemm_impl(const pa_gemm_args* a, cudaStream_t st) {
+  GemmPlan plan;
+  int rc = gemm_prepare(a, &plan);
+  if (rc) return rc;
+  const CUtensorMap& tmA = plan.tmA; const CUtensorMap& tmB = plan.tmB; const CUtensorMap& tmD = plan.tmD;
+  const GemmParams& p = plan.p;
+  const int bn = plan.bn, cl = plan.cl;
   switch (bn) {
     case 256: return launch_gemm_cl<256, 4>(cl, tmA, tmB, tmD, p, st);
     case 192: return launch_gemm_cl<192, 4>(cl, tmA, tmB, tmD, p, st);
@@ -224,7 +244,15 @@ int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
   return PA_OK;
 }
 
-int attn_launch(const AttnLaunch& a, cudaStream_t st) {
+struct AttnPlan {
+  CUtensorMap tq, tk, tv, to;
+  AttnParams p;
+  int smem;
+};
+
+int attn_prepare(const AttnLaunch& a, AttnPlan* plan) {
+  CUtensorMap& tq = plan->tq; CUtensorMap& tk = plan->tk; CUtensorMap& tv = plan->tv; CUtensorMap& to = plan->to;
+  AttnParams& p = plan->p;
   if (a.hd != 64 && a.hd != 32) return fail(PA_ERR_UNSUPPORTED, "attention core: head_dim %d unsupported (64 or 32)", a.hd);
   if (!(a.scale > 0.f)) return fail(PA_ERR_UNSUPPORTED, "attention core: scale must be > 0");
   if (a.ldo % 8 || a.o_col0 % 8 || a.o_group % 8 || (reinterpret_cast<uintptr_t>(a.o) & 15))
@@ -235,7 +263,8 @@ int attn_launch(const AttnLaunch& a, cudaStream_t st) {
   const int kb_max_multi = 256 - hd;
   const TmapSwizzle swz = hd == 64 ? TM_SWZ_128 : TM_SWZ_64;
 
-  AttnParams p = {};
+  p = AttnParams{};
+  p.wait_ctr = nullptr; p.signal_ctr = nullptr; p.wait_target = 0; p.wait_rows_per_group = 0; p.reverse_ctas = 0;
   p.H = a.H;
   p.q_col0 = a.q_col0; p.k_col0 = a.k_col0; p.v_col0 = a.v_col0;
   p.O = a.o; p.ldo = a.ldo; p.o_group = a.o_group; p.o_col0 = a.o_col0;
@@ -243,8 +272,6 @@ int attn_launch(const AttnLaunch& a, cudaStream_t st) {
   p.add_into_out = a.add_into_out;
   p.trace = g_gemm_trace;
   { const char* dbg = getenv("PA_ATTN_DEBUG"); p.debug_flags = dbg ? atoi(dbg) : 0; }
-  CUtensorMap tq, tk, tv;
-
   if (!a.windowed) {
     p.G = a.G; p.n_q = a.n_q; p.n_k = a.n_k;
     if (a.n_k <= 256) { p.nkb = 1; p.kb = (a.n_k + 15) / 16 * 16; }
@@ -302,7 +329,7 @@ int attn_launch(const AttnLaunch& a, cudaStream_t st) {
   const int smem = attn_smem_bytes(hd, a.windowed, p.nkb, p.kb, p.kb_rows, staged);
   if (smem > 227 * 1024) return fail(PA_ERR_UNSUPPORTED, "attention core: shared memory plan %d B too large", smem);
   // output map for the staged TMA-store epilogue (non-windowed): {columns, rows of a group, groups}, box {hd, 128, 1}
-  CUtensorMap to = tq;
+  to = tq;
   p.tma_store = 0;
   if (staged) {
     uint64_t dims[3] = {(uint64_t)a.ldo, (uint64_t)a.n_q, (uint64_t)a.G};
@@ -311,8 +338,19 @@ int attn_launch(const AttnLaunch& a, cudaStream_t st) {
     if ((rc = make_tmap_16b(&to, PA_DTYPE_F16, a.o, 3, dims, str, box, swz))) return rc;
     p.tma_store = 1;
   }
-  if (hd == 64) return a.windowed ? launch_attn_t<64, true>(tq, tk, tv, to, p, smem, st) : launch_attn_t<64, false>(tq, tk, tv, to, p, smem, st);
-  return a.windowed ? launch_attn_t<32, true>(tq, tk, tv, to, p, smem, st) : launch_attn_t<32, false>(tq, tk, tv, to, p, smem, st);
+  plan->smem = smem;
+  return PA_OK;
+}
+
+int attn_launch(const AttnLaunch& a, cudaStream_t st) {
+  AttnPlan plan;
+  int rc = attn_prepare(a, &plan);
+  if (rc) return rc;
+  const int hd = a.hd;
+  if (hd == 64) return a.windowed ? launch_attn_t<64, true>(plan.tq, plan.tk, plan.tv, plan.to, plan.p, plan.smem, st)
+                                  : launch_attn_t<64, false>(plan.tq, plan.tk, plan.tv, plan.to, plan.p, plan.smem, st);
+  return a.windowed ? launch_attn_t<32, true>(plan.tq, plan.tk, plan.tv, plan.to, plan.p, plan.smem, st)
+                    : launch_attn_t<32, false>(plan.tq, plan.tk, plan.tv, plan.to, plan.p, plan.smem, st);
 }
 
 int attn_impl(const pa_attn_args* a, cudaStream_t st) {
@@ -374,7 +412,7 @@ static int vit_check(const pa_vit_args* a) {
 size_t pa_vit_workspace_bytes(const pa_vit_args* a) {
   if (vit_check(a)) return 0;
   const size_t rows = (size_t)a->B * a->N;
-  return align_up(rows * 3 * a->C * 2, 1024) + align_up(rows * a->C * 2, 1024) + 1024;
+  return align_up(rows * 3 * a->C * 2, 1024) + align_up(rows * a->C * 2, 1024) + align_up(((rows + 127) / 128 + a->B) * 4, 1024) + 1024;
 }
 
 int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, void* stream) {
@@ -389,6 +427,69 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
   Arena ws(workspace);
   void* qkv = ws.take((size_t)rows * 3 * C * 2);
   void* obuf = ws.take((size_t)rows * C * 2);
+  int* counters = reinterpret_cast<int*>(ws.take(((size_t)(rows + 127) / 128 + a->B) * sizeof(int)));
+  if (getenv("PA_VIT_FUSED") && a->N <= 256 && a->out_dtype != PA_DTYPE_F32 + 99) {
+    // ---- opt-in: the whole forward as ONE launch (pa_fused.cuh), phases chained by dependency counters
+    if ((rc = current_device_check())) return rc;
+    const int n_mt = (int)((rows + 127) / 128);
+    PA_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)(n_mt + a->B) * sizeof(int), st));
+    pa_gemm_args g1 = {};
+    g1.a_dtype = a->dtype; g1.b_dtype = a->dtype; g1.out_dtype = PA_DTYPE_F16;
+    g1.M = (int)rows; g1.N = 3 * C; g1.K = C; g1.Z = 1;
+    g1.A = a->x; g1.lda = C; g1.B = a->qkv_weight; g1.ldb = C; g1.D = qkv; g1.ldd = 3 * C;
+    g1.bias = a->qkv_bias; g1.bias_mode = a->qkv_bias ? 1 : 0;
+    GemmPlan p1;
+    if ((rc = gemm_prepare(&g1, &p1, FUSED_BN1, -2))) return rc;
+    AttnLaunch al = {};
+    al.hd = 64; al.G = a->B; al.H = a->H; al.n_q = a->N; al.n_k = a->N;
+    al.q = qkv; al.ldq = 3 * C; al.q_group = (long long)a->N * 3 * C; al.q_col0 = 0;
+    al.k = qkv; al.v = qkv; al.ldk = 3 * C; al.k_group = (long long)a->N * 3 * C; al.k_col0 = C; al.v_col0 = 2 * C;
+    al.o = obuf; al.ldo = C; al.o_group = (long long)a->N * C; al.o_col0 = 0;
+    al.scale = a->scale;
+    AttnPlan pa_;
+    if ((rc = attn_prepare(al, &pa_))) return rc;
+    if (!pa_.p.tma_store) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(fused): staged attention epilogue does not fit");
+    pa_gemm_args g2 = {};
+    g2.a_dtype = PA_DTYPE_F16; g2.b_dtype = PA_DTYPE_F16; g2.out_dtype = a->out_dtype;
+    g2.M = (int)rows; g2.N = C; g2.K = C; g2.Z = 1;
+    g2.A = obuf; g2.lda = C; g2.B = a->proj_weight; g2.ldb = C; g2.D = a->y; g2.ldd = C;
+    g2.bias = a->proj_bias; g2.bias_mode = a->proj_bias ? 1 : 0;
+    GemmPlan p2;
+    if ((rc = gemm_prepare(&g2, &p2, FUSED_BN2, -2))) return rc;
+    if (!p1.p.tma_store || !p2.p.tma_store) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(fused): outputs must be TMA-storable");
+    VitFusedParams fp;
+    fp.g1 = p1.p; fp.at = pa_.p; fp.g2 = p2.p;
+    fp.g1.m_groups = (fp.g1.m_tiles + 1) / 2; fp.g1.balanced = 0;
+    fp.g2.m_groups = (fp.g2.m_tiles + 1) / 2; fp.g2.balanced = 0;
+    if (g_gemm_trace) { fp.g1.trace = g_gemm_trace; fp.at.trace = g_gemm_trace + 512; fp.g2.trace = g_gemm_trace + 1024; }
+    fp.at.reverse_ctas = 1; fp.g2.reverse_workers = 1;            // per-phase remainders land on different CTAs
+    fp.g1.signal_ctr = counters;                                   // per 128-row tile of qkv
+    fp.at.wait_ctr = counters; fp.at.wait_target = fp.g1.n_tiles; fp.at.wait_rows_per_group = a->N;
+    fp.at.signal_ctr = counters + n_mt;                            // per image
+    fp.g2.wait_ctr = counters + n_mt; fp.g2.wait_rows = a->N; fp.g2.wait_target = a->H * fp.at.q_tiles;
+    const int smem = vit_fused_smem_bytes(fp.at.kb);
+    if (smem > 227 * 1024) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(fused): shared memory plan %d B too large", smem);
+    static int attr_done[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_done[dev & 63] < smem) {
+      PA_CUDA_OK(cudaFuncSetAttribute(vit_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_done[dev & 63] = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((num_sms() / 2) * 2);
+    cfg.blockDim = dim3(ATTN_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    PA_CUDA_OK(cudaLaunchKernelEx(&cfg, vit_fused_kernel, p1.tmA, p1.tmB, p1.tmD, pa_.tq, pa_.tk, pa_.tv, pa_.to, p2.tmA, p2.tmB,
+                                  p2.tmD, fp));
+    launch_counter()++;
+    return PA_OK;
+  }
   // 1. qkv[B*N, 3C] = x Wqkv^T (+b)          (ViT.py:81)
   if ((rc = linear(a->x, a->dtype, C, a->qkv_weight, a->dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
   // 2. per (b,h): softmax(q k^T scale) v       (ViT.py:83-86), O as [B*N, C] with column h*64+d

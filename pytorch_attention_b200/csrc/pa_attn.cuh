@@ -44,6 +44,12 @@ struct AttnParams {
   long long* trace;     // debug: clock64 stamps of CTA 0 ([item][16]), or nullptr
   int tma_store;        // non-windowed: output tile goes through smem + TMA store (tmO valid)
   int debug_flags;      // timing experiments only (env PA_ATTN_DEBUG): 1 = no MUFU in pass 2, 2 = no P store, 4 = skip pass 1
+  // dependency hooks of the fused single-launch kernels (nullptr = none)
+  const int* wait_ctr;  // before loading a unit of group g: wait_ctr[t] >= wait_target for the 128-row tiles t covering its rows
+  int wait_target;
+  long long wait_rows_per_group;   // rows of the Q/K/V buffer per group (n_q == n_k assumed by the hook)
+  int* signal_ctr;      // after a (head, query tile) of group g has been stored completely: signal_ctr[g] += 1
+  int reverse_ctas;     // fused kernels: CTA c takes the item sequence of CTA (grid-1-c), so per-phase remainders land on different CTAs
 };
 
 #define ATTN_TRACE(seq, slot_) do { if (p.trace != nullptr && blockIdx.x == 0 && (seq) < 32) p.trace[(seq) * 16 + (slot_)] = clock64(); } while (0)
@@ -143,21 +149,32 @@ __device__ __forceinline__ void pack_stage(const float (&e)[16], uint32_t (&pk)[
   }
 }
 
+__device__ __forceinline__ void attn_init_barriers(uint64_t* bars) {     // one thread; bars: 16 mbarriers
+  for (int i = 0; i < 2; ++i) {
+    mbar_init(&bars[0 + i], 1);    // q_full
+    mbar_init(&bars[2 + i], 1);    // q_empty
+    mbar_init(&bars[4 + i], 1);    // kv_full
+    mbar_init(&bars[6 + i], 1);    // kv_empty
+    mbar_init(&bars[8 + i], 1);    // s_full
+    mbar_init(&bars[10 + i], 8);   // p_full
+    mbar_init(&bars[12 + i], 1);   // o_full
+    mbar_init(&bars[14 + i], 8);   // slot_empty
+  }
+}
+
+// All roles of one CTA over its whole item sequence.  Barriers initialised + visible and TMEM (512 columns) allocated
+// before the call; every thread of the CTA calls it.
 template <int HD, bool WINDOWED>
-__global__ void __launch_bounds__(ATTN_THREADS, 1)
-attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
-                 const AttnParams p) {
+__device__ __forceinline__ void attn_run(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                                         const CUtensorMap& tmO, const AttnParams& p, uint8_t* smem, uint64_t* bars,
+                                         uint32_t tmem_base) {
   using Cfg = AttnCfg<HD>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int q_rows = WINDOWED ? attn_q_rows(true, p.nkb, p.kb_rows) : 256;
   const int q_bytes = q_rows * Cfg::ROW_BYTES;          // one Q buffer
   const int kvb_bytes = p.kb * Cfg::ROW_BYTES;          // one K (or V) block buffer
   uint8_t* q_smem = smem;                               // [2][q_bytes]
   uint8_t* kv_smem = smem + 2 * q_bytes;                // [2 stages][K | V]
   uint8_t* o_smem = kv_smem + 4 * kvb_bytes;            // [2 slots][128 rows x HD fp16] output staging (non-windowed)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(o_smem + attn_ostage_bytes(HD, p.tma_store != 0));
   uint64_t* q_full = bars;            // [2] TMA -> MMA
   uint64_t* q_empty = bars + 2;       // [2] MMA -> TMA
   uint64_t* kv_full = bars + 4;       // [2]
@@ -166,50 +183,16 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* p_full = bars + 10;       // [2] softmax(slot) -> MMA: P written (and O rescaled)
   uint64_t* o_full = bars + 12;       // [2] MMA -> softmax(slot): PV of the block retired
   uint64_t* slot_empty = bars + 14;   // [2] epilogue(slot) -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  if (WINDOWED) {
-    // rows never touched by TMA (tile padding beyond the window) must read as finite zeros
-    uint4* z = reinterpret_cast<uint4*>(smem);
-    const int n16 = (2 * q_bytes + 4 * kvb_bytes) / 16;
-    for (int i = threadIdx.x; i < n16; i += ATTN_THREADS) z[i] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async_smem();
-  }
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 8);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&slot_empty[i], 8);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  int pend_sig = -1;                  // fused kernels: group whose output tile is stored but not yet published (slot leader)
 
   if (warp == 0) {
     // ===================== TMA producer (warp converged; one elected lane issues) =====================
     int qb = 0, st = 0;
     uint32_t qph = 0, kph = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    for (int item = (p.reverse_ctas ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x); item < p.items; item += gridDim.x) {
       const int pr = item % p.pairs;
       const int gh = item / p.pairs;
       const int h = gh % p.H, g = gh / p.H;
@@ -220,6 +203,14 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int img = g / p.nWin, w = g - img * p.nWin;
         c3 = w % p.nJ;                                  // window column
         c4 = img * (p.nWin / p.nJ) + w / p.nJ;          // image * nI + window row
+      }
+      if (!WINDOWED && p.wait_ctr != nullptr) {
+        // fused kernels: the q/k/v rows of group g are produced by an earlier phase on other SMs
+        if (elect_one()) {
+          const long long r0 = (long long)g * p.wait_rows_per_group, r1 = r0 + p.n_q - 1;
+          for (int t = (int)(r0 >> 7); t <= (int)(r1 >> 7); ++t) wait_counter_ge(p.wait_ctr + t, p.wait_target);
+        }
+        __syncwarp();
       }
       mbar_wait(&q_empty[qb], qph ^ 1);
       if (elect_one()) {
@@ -299,7 +290,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       pend = false;
     };
 
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++iseq) {
+    for (int item = (p.reverse_ctas ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x); item < p.items; item += gridDim.x, ++iseq) {
       const int pr = item % p.pairs;
       const int nslots = ((2 * pr + 1) < p.q_tiles) ? 2 : 1;
       const uint32_t qbuf = q_base + qb * q_bytes;
@@ -393,7 +384,8 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint32_t sf_ph = 0, of_ph = 0;
     int iseq = -1;
     const bool tracer = (q == 0 && hf == 0 && lane == 0);
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    pend_sig = -1;
+    for (int item = (p.reverse_ctas ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x); item < p.items; item += gridDim.x) {
       ++iseq;
       const int pr = item % p.pairs;
       const int gh = item / p.pairs;
@@ -486,7 +478,16 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (lane == 0) mbar_arrive(&slot_empty[slot]);
       if (!WINDOWED && p.tma_store) {
         // the staging tile is free once the PREVIOUS item's bulk store has read it (long ago: off the critical path)
-        if (sw == slot * 8 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (sw == slot * 8 && lane == 0) {
+          if (p.signal_ctr != nullptr && pend_sig >= 0) {     // previous tile of this slot: stores complete -> publish
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __threadfence();
+            atomicAdd(p.signal_ctr + pend_sig, 1);
+          } else {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          pend_sig = g;
+        }
         asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");
       }
       if (warp_active) {
@@ -553,7 +554,52 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   }
 
-  if (!WINDOWED && p.tma_store && (warp == 2 || warp == 10) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (!WINDOWED && p.tma_store && (warp == 2 || warp == 10) && lane == 0) {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (p.signal_ctr != nullptr && pend_sig >= 0) { __threadfence(); atomicAdd(p.signal_ctr + pend_sig, 1); }
+  }
+}
+
+template <int HD, bool WINDOWED>
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
+attn_core_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                 const AttnParams p) {
+  using Cfg = AttnCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int q_rows = WINDOWED ? attn_q_rows(true, p.nkb, p.kb_rows) : 256;
+  const int data_bytes = 2 * q_rows * Cfg::ROW_BYTES + 4 * p.kb * Cfg::ROW_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + data_bytes + attn_ostage_bytes(HD, p.tma_store != 0));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (WINDOWED) {
+    // rows never touched by TMA (tile padding beyond the window) must read as finite zeros
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < data_bytes / 16; i += ATTN_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    attn_init_barriers(bars);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  attn_run<HD, WINDOWED>(tmQ, tmK, tmV, tmO, p, smem, bars, tmem_base);
+
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

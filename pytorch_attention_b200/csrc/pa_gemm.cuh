@@ -31,6 +31,11 @@ struct GemmParams {
   long long ldr, r_batch;
   int res_dtype;
   int tma_store;           // 1: epilogue goes through smem + TMA store (tmD valid)
+  // dependency hooks for the fused single-launch kernels (nullptr = none).  Counters live in global memory.
+  const int* wait_ctr;     // before loading A rows [r0, r1] of a tile: wait_ctr[r / wait_rows] >= wait_target for both ends
+  int wait_rows, wait_target;
+  int* signal_ctr;         // after a CTA's 128-row tile has been stored completely: signal_ctr[m-tile] += 1
+  int reverse_workers;     // fused kernels: worker w walks the tile sequence of worker (n-1-w)
   int balanced;            // PAIR + BLOCK_N 256 only: balanced contiguous partition of 64-column units (see TileWalk)
   int n_units;             // ceil(N / 64)
   uint32_t idesc;
@@ -117,54 +122,44 @@ struct TileWalk {
 //   full[stage]   leader's barrier, expect_tx = bytes of BOTH CTAs (every TMA load signals the leader's barrier)
 //   empty[stage]  each CTA's own barrier, released by the leader's multicast tcgen05.commit
 //   tfull[acc]    each CTA's own barrier (multicast commit);  tempty[acc]: leader's, 8 arrivals (4 epilogue warps x 2 CTAs)
-template <int BLOCK_N, int STAGES, int CLUSTER, bool PAIR = false>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+template <int STAGES, int CLUSTER, bool PAIR>
+__device__ __forceinline__ void gemm_init_barriers(uint64_t* bars) {      // one thread; bars: [2*STAGES + 4] mbarriers
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  for (int i = 0; i < STAGES; ++i) {
+    mbar_init(&full_bar[i], 1);
+    mbar_init(&empty_bar[i], PAIR ? 1 : CLUSTER);
+  }
+  for (int i = 0; i < 2; ++i) {
+    mbar_init(&tfull_bar[i], 1);
+    mbar_init(&tempty_bar[i], PAIR ? 8 : 4);
+  }
+}
+
+// The three roles of one CTA (warp 0 producer, warp 1 MMA issuer, warps 4-7 epilogue) over its whole tile sequence.
+// Barriers must be initialised and visible (cluster-wide when CLUSTER > 1) and TMEM allocated before the call.
+// LEAN: compile out the rarely used epilogue variants (row bias, residual, unaligned-output fallback) -- the fused kernels
+// run 20 warps per CTA and have only 96 registers per thread.
+template <int BLOCK_N, int STAGES, int CLUSTER, bool PAIR, bool LEAN = false>
+__device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                                         const GemmParams& p, uint8_t* smem, uint64_t* bars, uint32_t tmem_base) {
   static_assert(!PAIR || CLUSTER == 2, "cta_group::2 needs a cluster of exactly two CTAs");
   using Cfg = GemmCfg<BLOCK_N, STAGES, PAIR>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFFSET);
+  uint64_t* full_bar = bars;
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;    // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   const int crank = (CLUSTER > 1) ? (int)cluster_ctarank() : 0;
-  const int cid = blockIdx.x / CLUSTER;                  // cluster index = persistent worker index
   const int ncl = gridDim.x / CLUSTER;
+  const int cid = p.reverse_workers ? ncl - 1 - (int)(blockIdx.x / CLUSTER) : (int)(blockIdx.x / CLUSTER);   // persistent worker index
   constexpr uint16_t CMASK = (uint16_t)((1u << CLUSTER) - 1);
   constexpr int B_SLICE_ROWS = BLOCK_N / CLUSTER;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    if (p.tma_store) tma_prefetch_desc(&tmD);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], PAIR ? 1 : CLUSTER);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], PAIR ? 8 : 4);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    if (PAIR) { tmem_alloc2(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish2(); }
-    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (CLUSTER > 1) cluster_sync_all();     // peers' barriers must be initialised before any remote arrive / multicast
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
@@ -175,6 +170,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (; tw.next(); ++tseq) {
       const int z = tw.z;
       const int mt = tw.mg * CLUSTER + crank;
+      if (p.wait_ctr != nullptr) {
+        // fused kernels: the rows of this A tile are produced by an earlier phase on other SMs
+        if (elect_one()) {
+          const int r0 = mt * GEMM_BLOCK_M, r1 = min(r0 + GEMM_BLOCK_M, p.M) - 1;
+          if (r0 < p.M) {
+            const int g0 = r0 / p.wait_rows, g1 = r1 / p.wait_rows;
+            for (int g = g0; g <= g1; ++g) wait_counter_ge(p.wait_ctr + g, p.wait_target);
+          }
+        }
+        __syncwarp();
+      }
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -251,8 +257,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue =====================
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue (warps 4-7; wider CTAs of the fused kernels leave the rest idle here) ==========
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int trow = q * 32 + lane;         // row inside the tile
     const bool leader = (warp == 4 && lane == 0);
@@ -261,6 +267,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* cbuf = smem + Cfg::C_OFFSET;
     int acc = 0, cb = 0, tseq = 0;
     uint32_t acc_phase = 0;
+    int pending_mt = -1;                     // fused kernels: tile whose stores are in flight and not yet published
     TileWalk tw(p, cid, ncl, BLOCK_N);
     for (; tw.next(); ++tseq) {
       const int z = tw.z;
@@ -269,10 +276,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int col0 = tw.col0;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (p.signal_ctr != nullptr && leader && pending_mt >= 0) {
+        if (pending_mt < p.m_tiles) signal_counter(p.signal_ctr + pending_mt);   // its stores were issued a whole mainloop ago
+      }
+      pending_mt = mt;
       if (leader) trace_stamp(p, tseq, 4);
       const uint32_t t_base = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
       const bool row_ok = row < p.M;
-      const float bias_m = (p.bias_mode == 2 && row_ok) ? p.bias[row] : 0.f;
+      const float bias_m = (!LEAN && p.bias_mode == 2 && row_ok) ? p.bias[row] : 0.f;
       const long long d_off = (long long)z * p.d_batch + (long long)row * p.ldd;
       float* sbias = reinterpret_cast<float*>(smem + Cfg::BIAS_OFFSET);
       if (p.bias_mode == 1) {
@@ -299,7 +310,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
           }
         }
-        if (p.residual != nullptr && row_ok) {
+        if (!LEAN && p.residual != nullptr && row_ok) {
           const long long r_off = (long long)z * p.r_batch + (long long)row * p.ldr + col;
           if (p.res_dtype == 2) {
             const float* rp = reinterpret_cast<const float*>(p.residual) + r_off;
@@ -332,7 +343,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        if (p.tma_store) {
+        if (LEAN || p.tma_store) {
           // ---- staged path: this 128 x 32 sub-tile -> swizzled smem -> one TMA store
           uint8_t* buf = cbuf + cb * GEMM_CSTAGE_BYTES;
           if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer cb's previous store has been read
@@ -397,8 +408,45 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output bytes committed before exit
+    if (leader) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output bytes committed before exit
+      if (p.signal_ctr != nullptr && pending_mt >= 0 && pending_mt < p.m_tiles) signal_counter(p.signal_ctr + pending_mt);
+    }
   }
+
+}
+
+template <int BLOCK_N, int STAGES, int CLUSTER, bool PAIR = false>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N, STAGES, PAIR>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFFSET);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmD);
+  }
+  if (warp == 1 && lane == 0) {
+    gemm_init_barriers<STAGES, CLUSTER, PAIR>(bars);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    if (PAIR) { tmem_alloc2(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();     // peers' barriers must be initialised before any remote arrive / multicast
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  gemm_run<BLOCK_N, STAGES, CLUSTER, PAIR>(tmA, tmB, tmD, p, smem, bars, tmem_base);
 
   tc_fence_before();
   __syncthreads();

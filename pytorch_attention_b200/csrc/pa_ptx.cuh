@@ -287,6 +287,26 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- cross-CTA dependency counters (fused kernels)
+// acquire-spin on a global counter (elected lane of a converged warp), then order the following TMA (async proxy) loads
+__device__ __forceinline__ void wait_counter_ge(const int* ctr, int target) {
+  int v;
+  long long t0 = clock64();
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= target) break;
+    __nanosleep(200);
+    if (clock64() - t0 > PA_WATCHDOG_CYCLES) { printf("pa: dependency watchdog: block %d ctr %p = %d < %d\n", (int)blockIdx.x, ctr, v, target); __trap(); }
+  } while (true);
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+// publish: all bulk stores of this thread are complete -> release the counter
+__device__ __forceinline__ void signal_counter(int* ctr) {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __threadfence();
+  atomicAdd(ctr, 1);
+}
+
 // ---------------------------------------------------------------- descriptors
 // Operand element formats for kind::f16
 enum : uint32_t { PA_F16 = 0, PA_BF16 = 1 };

@@ -121,3 +121,27 @@ def test_swap_into_reference_shaped_block():
     ref_like = torch.nn.ModuleDict(dict(qkv=torch.nn.Linear(128, 384, bias=False), proj=torch.nn.Linear(128, 128)))
     m = pa.ViTAttention(128, 2)
     m.load_state_dict(ref_like.state_dict())
+
+
+@pytest.mark.parametrize("B,C,H,N", [(64, 768, 12, 197), (5, 128, 2, 197), (3, 256, 4, 64), (16, 1024, 16, 197)])
+def test_vit_fused_single_launch_matches_three_launch_path(B, C, H, N, monkeypatch):
+    """PA_VIT_FUSED=1: the whole forward as ONE launch (phases chained by dependency counters).  Same arithmetic in the
+    same order as the three-launch path -> bit-identical output; repeated runs stay identical (no race)."""
+    from pytorch_attention_b200 import _lib
+    m, x = _fresh(C, H, B, N, 11, qkv_bias=(C == 128))
+    m = m.cuda()
+    xg = x.cuda()
+    with torch.no_grad():
+        y3 = m(xg)
+        monkeypatch.setenv("PA_VIT_FUSED", "1")
+        n0 = _lib.launch_count()
+        y1 = m(xg)
+        assert _lib.launch_count() - n0 == 1
+        for _ in range(5):
+            assert torch.equal(m(xg), y1)
+        monkeypatch.delenv("PA_VIT_FUSED")
+    assert torch.equal(y1, y3)
+    if B <= 5:
+        sd = {k: v.float().cpu() for k, v in m.state_dict().items()}
+        ref = vit_attention(x.float(), sd["qkv.weight"], sd.get("qkv.bias"), sd["proj.weight"], sd["proj.bias"], H)
+        assert rel_fro(y1.float().cpu(), ref) < TOL
