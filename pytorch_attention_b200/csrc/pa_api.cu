@@ -40,7 +40,11 @@ int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
   p.m_groups = (p.m_tiles + CL - 1) / CL;
   if (!(PAIR && BN == 256)) p.balanced = 0;
   const int supertiles = p.m_groups * p.n_tiles * p.Z;
-  const int max_clusters = num_sms() / CL;
+  int max_clusters = num_sms() / CL;
+  if (const char* env = getenv("PA_GEMM_MAXWORKERS")) {   // experiment: contention vs number of active workers
+    const int v = atoi(env);
+    if (v > 0 && v < max_clusters) max_clusters = v;
+  }
   const int nclusters = supertiles < max_clusters ? supertiles : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * CL);
@@ -163,7 +167,7 @@ int gemm_prepare(const pa_gemm_args* a, GemmPlan* plan, int force_bn = 0, int fo
   p.idesc = make_idesc(pair ? 256 : 128, bn, a->a_dtype, a->b_dtype, 0, 0);
   p.trace = g_gemm_trace;
   p.balanced = balanced ? 1 : 0;
-  p.wait_ctr = nullptr; p.wait_rows = 1; p.wait_target = 0; p.signal_ctr = nullptr; p.reverse_workers = 0;
+  p.wait_ctr = nullptr; p.wait_rows = 1; p.wait_target = 0; p.signal_ctr = nullptr; p.worker_shift = 0;
   p.n_units = (a->N + 63) / 64;
   { const char* dbg = getenv("PA_GEMM_DEBUG"); p.debug_flags = dbg ? atoi(dbg) : 0; }
   // output map for the staged TMA-store epilogue (128 x 32 sub-tiles); needs 16-byte aligned base and pitches
@@ -264,7 +268,7 @@ int attn_prepare(const AttnLaunch& a, AttnPlan* plan) {
   const TmapSwizzle swz = hd == 64 ? TM_SWZ_128 : TM_SWZ_64;
 
   p = AttnParams{};
-  p.wait_ctr = nullptr; p.signal_ctr = nullptr; p.wait_target = 0; p.wait_rows_per_group = 0; p.reverse_ctas = 0;
+  p.wait_ctr = nullptr; p.signal_ctr = nullptr; p.wait_target = 0; p.wait_rows_per_group = 0; p.cta_shift = 0;
   p.H = a.H;
   p.q_col0 = a.q_col0; p.k_col0 = a.k_col0; p.v_col0 = a.v_col0;
   p.O = a.o; p.ldo = a.ldo; p.o_group = a.o_group; p.o_col0 = a.o_col0;
@@ -428,11 +432,17 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
   void* qkv = ws.take((size_t)rows * 3 * C * 2);
   void* obuf = ws.take((size_t)rows * C * 2);
   int* counters = reinterpret_cast<int*>(ws.take(((size_t)(rows + 127) / 128 + a->B) * sizeof(int)));
-  if (getenv("PA_VIT_FUSED") && a->N <= 256 && a->out_dtype != PA_DTYPE_F32 + 99) {
-    // ---- opt-in: the whole forward as ONE launch (pa_fused.cuh), phases chained by dependency counters
+  // ---- the whole forward as ONE launch (pa_fused.cuh), phases chained by dependency counters.  Default whenever the shape
+  //      qualifies (single key block, staged epilogues); PA_VIT_FUSED=0 selects the three-launch path, =1 makes a
+  //      non-qualifying shape an error instead of a silent switch to the three launches.
+  const char* fused_env = getenv("PA_VIT_FUSED");
+  const bool fused_forced = fused_env && atoi(fused_env) != 0;
+  const bool fused_wanted = fused_env ? fused_forced : true;
+  bool fused_ok = fused_wanted && a->N <= 256;
+  if (fused_forced && !fused_ok) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(fused): N=%d > 256 needs several key blocks", a->N);
+  if (fused_ok) {
     if ((rc = current_device_check())) return rc;
     const int n_mt = (int)((rows + 127) / 128);
-    PA_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)(n_mt + a->B) * sizeof(int), st));
     pa_gemm_args g1 = {};
     g1.a_dtype = a->dtype; g1.b_dtype = a->dtype; g1.out_dtype = PA_DTYPE_F16;
     g1.M = (int)rows; g1.N = 3 * C; g1.K = C; g1.Z = 1;
@@ -448,7 +458,10 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
     al.scale = a->scale;
     AttnPlan pa_;
     if ((rc = attn_prepare(al, &pa_))) return rc;
-    if (!pa_.p.tma_store) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(fused): staged attention epilogue does not fit");
+    if (!pa_.p.tma_store) {
+      if (fused_forced) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(fused): staged attention epilogue does not fit");
+      fused_ok = false;
+    }
     pa_gemm_args g2 = {};
     g2.a_dtype = PA_DTYPE_F16; g2.b_dtype = PA_DTYPE_F16; g2.out_dtype = a->out_dtype;
     g2.M = (int)rows; g2.N = C; g2.K = C; g2.Z = 1;
@@ -456,19 +469,33 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
     g2.bias = a->proj_bias; g2.bias_mode = a->proj_bias ? 1 : 0;
     GemmPlan p2;
     if ((rc = gemm_prepare(&g2, &p2, FUSED_BN2, -2))) return rc;
-    if (!p1.p.tma_store || !p2.p.tma_store) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(fused): outputs must be TMA-storable");
+    const int smem = vit_fused_smem_bytes(pa_.p.kb);
+    if (!p1.p.tma_store || !p2.p.tma_store || smem > 227 * 1024) {
+      if (fused_forced) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(fused): outputs must be TMA-storable and the plan (%d B) must fit", smem);
+      fused_ok = false;
+    }
+    if (fused_ok) {
+    PA_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)(n_mt + a->B) * sizeof(int), st));
     VitFusedParams fp;
     fp.g1 = p1.p; fp.at = pa_.p; fp.g2 = p2.p;
     fp.g1.m_groups = (fp.g1.m_tiles + 1) / 2; fp.g1.balanced = 0;
     fp.g2.m_groups = (fp.g2.m_tiles + 1) / 2; fp.g2.balanced = 0;
     if (g_gemm_trace) { fp.g1.trace = g_gemm_trace; fp.at.trace = g_gemm_trace + 512; fp.g2.trace = g_gemm_trace + 1024; }
-    fp.at.reverse_ctas = 1; fp.g2.reverse_workers = 1;            // per-phase remainders land on different CTAs
+    {
+      // static balance: each phase's remainder units (the CTAs that get one unit more than the others) are placed on
+      // different CTAs -- qkv extras on pairs [0, r1), attention extras on the CTAs after them, and the proj phase
+      // rotated so that its light pairs are the ones that were heavy before
+      const int grid = (num_sms() / 2) * 2, ncl = grid / 2;
+      const int r1 = (fp.g1.m_groups * fp.g1.n_tiles) % ncl;
+      const int r3 = (fp.g2.m_groups * fp.g2.n_tiles) % ncl;
+      fp.at.cta_shift = (2 * r1) % grid;
+      fp.g2.worker_shift = r3;
+    }
     fp.g1.signal_ctr = counters;                                   // per 128-row tile of qkv
-    fp.at.wait_ctr = counters; fp.at.wait_target = fp.g1.n_tiles; fp.at.wait_rows_per_group = a->N;
+    fp.at.wait_ctr = counters; fp.at.wait_target = fp.g1.n_tiles * FUSED_ESETS;   // every epilogue set of every column tile publishes
+    fp.at.wait_rows_per_group = a->N;
     fp.at.signal_ctr = counters + n_mt;                            // per image
     fp.g2.wait_ctr = counters + n_mt; fp.g2.wait_rows = a->N; fp.g2.wait_target = a->H * fp.at.q_tiles;
-    const int smem = vit_fused_smem_bytes(fp.at.kb);
-    if (smem > 227 * 1024) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(fused): shared memory plan %d B too large", smem);
     static int attr_done[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -489,7 +516,9 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
                                   p2.tmD, fp));
     launch_counter()++;
     return PA_OK;
+    }
   }
+  // ---- three launches (any N; also the reference point the fused kernel is tested against)
   // 1. qkv[B*N, 3C] = x Wqkv^T (+b)          (ViT.py:81)
   if ((rc = linear(a->x, a->dtype, C, a->qkv_weight, a->dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
   // 2. per (b,h): softmax(q k^T scale) v       (ViT.py:83-86), O as [B*N, C] with column h*64+d

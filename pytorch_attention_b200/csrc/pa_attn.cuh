@@ -49,7 +49,8 @@ struct AttnParams {
   int wait_target;
   long long wait_rows_per_group;   // rows of the Q/K/V buffer per group (n_q == n_k assumed by the hook)
   int* signal_ctr;      // after a (head, query tile) of group g has been stored completely: signal_ctr[g] += 1
-  int reverse_ctas;     // fused kernels: CTA c takes the item sequence of CTA (grid-1-c), so per-phase remainders land on different CTAs
+  int cta_shift;        // fused kernels: CTA c walks the item sequence of virtual CTA (c - cta_shift) mod grid, so that the
+                        // CTAs holding this phase's remainder items are not the ones holding the other phases' remainders
 };
 
 #define ATTN_TRACE(seq, slot_) do { if (p.trace != nullptr && blockIdx.x == 0 && (seq) < 32) p.trace[(seq) * 16 + (slot_)] = clock64(); } while (0)
@@ -192,7 +193,7 @@ __device__ __forceinline__ void attn_run(const CUtensorMap& tmQ, const CUtensorM
     // ===================== TMA producer (warp converged; one elected lane issues) =====================
     int qb = 0, st = 0;
     uint32_t qph = 0, kph = 0;
-    for (int item = (p.reverse_ctas ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x); item < p.items; item += gridDim.x) {
+    for (int item = (int)((blockIdx.x + gridDim.x - p.cta_shift) % gridDim.x); item < p.items; item += gridDim.x) {
       const int pr = item % p.pairs;
       const int gh = item / p.pairs;
       const int h = gh % p.H, g = gh / p.H;
@@ -290,7 +291,7 @@ __device__ __forceinline__ void attn_run(const CUtensorMap& tmQ, const CUtensorM
       pend = false;
     };
 
-    for (int item = (p.reverse_ctas ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x); item < p.items; item += gridDim.x, ++iseq) {
+    for (int item = (int)((blockIdx.x + gridDim.x - p.cta_shift) % gridDim.x); item < p.items; item += gridDim.x, ++iseq) {
       const int pr = item % p.pairs;
       const int nslots = ((2 * pr + 1) < p.q_tiles) ? 2 : 1;
       const uint32_t qbuf = q_base + qb * q_bytes;
@@ -385,7 +386,7 @@ __device__ __forceinline__ void attn_run(const CUtensorMap& tmQ, const CUtensorM
     int iseq = -1;
     const bool tracer = (q == 0 && hf == 0 && lane == 0);
     pend_sig = -1;
-    for (int item = (p.reverse_ctas ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x); item < p.items; item += gridDim.x) {
+    for (int item = (int)((blockIdx.x + gridDim.x - p.cta_shift) % gridDim.x); item < p.items; item += gridDim.x) {
       ++iseq;
       const int pr = item % p.pairs;
       const int gh = item / p.pairs;

@@ -24,6 +24,7 @@ struct VitFusedParams {
 };
 
 constexpr int FUSED_BN1 = 256, FUSED_ST1 = 6;   // qkv: 256 x 256 pair tiles
+constexpr int FUSED_ESETS = 2;                   // GEMM phases drain accumulators with warps 4-11 (the CTA has 20 warps anyway)
 constexpr int FUSED_BN2 = 192, FUSED_ST2 = 5;   // proj: 256 x 192 pair tiles
 
 __host__ __device__ inline int vit_fused_data_bytes(int kb) {
@@ -59,9 +60,9 @@ vit_fused_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); tma_prefetch_desc(&tmD2);
   }
   if (warp == 1 && lane == 0) {
-    gemm_init_barriers<FUSED_ST1, 2, true>(bars1);
+    gemm_init_barriers<FUSED_ST1, 2, true, FUSED_ESETS>(bars1);
     attn_init_barriers(barsA);
-    gemm_init_barriers<FUSED_ST2, 2, true>(bars2);
+    gemm_init_barriers<FUSED_ST2, 2, true, FUSED_ESETS>(bars2);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -83,7 +84,7 @@ vit_fused_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   stamp(0);
 
   // ---- phase 1: qkv projection
-  gemm_run<FUSED_BN1, FUSED_ST1, 2, true, true>(tmA1, tmB1, tmD1, P.g1, smem, bars1, tmem_base);
+  gemm_run<FUSED_BN1, FUSED_ST1, 2, true, true, FUSED_ESETS>(tmA1, tmB1, tmD1, P.g1, smem, bars1, tmem_base);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();          // the pair's MMAs read both CTAs' shared memory: nobody reuses it before both are done
@@ -99,7 +100,7 @@ vit_fused_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   stamp(2);
 
   // ---- phase 3: output projection
-  gemm_run<FUSED_BN2, FUSED_ST2, 2, true, true>(tmA2, tmB2, tmD2, P.g2, smem, bars2, tmem_base);
+  gemm_run<FUSED_BN2, FUSED_ST2, 2, true, true, FUSED_ESETS>(tmA2, tmB2, tmD2, P.g2, smem, bars2, tmem_base);
 
   tc_fence_before();
   __syncthreads();

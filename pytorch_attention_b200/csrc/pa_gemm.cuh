@@ -35,7 +35,7 @@ struct GemmParams {
   const int* wait_ctr;     // before loading A rows [r0, r1] of a tile: wait_ctr[r / wait_rows] >= wait_target for both ends
   int wait_rows, wait_target;
   int* signal_ctr;         // after a CTA's 128-row tile has been stored completely: signal_ctr[m-tile] += 1
-  int reverse_workers;     // fused kernels: worker w walks the tile sequence of worker (n-1-w)
+  int worker_shift;        // fused kernels: worker w walks the tile sequence of virtual worker (w + worker_shift) mod n
   int balanced;            // PAIR + BLOCK_N 256 only: balanced contiguous partition of 64-column units (see TileWalk)
   int n_units;             // ceil(N / 64)
   uint32_t idesc;
@@ -47,6 +47,13 @@ struct GemmParams {
 //              3 last MMA of tile issued | 4 epilogue: accumulator ready | 5 epilogue: tile drained | 6 producer: first load of tile issued
 __device__ __forceinline__ void trace_stamp(const GemmParams& p, int tile_seq, int slot) {
   if (p.trace != nullptr && blockIdx.x == 0 && tile_seq < 64) p.trace[tile_seq * 8 + slot] = clock64();
+}
+// steps inside the epilogue of tile 2 (warp 4 lane 0): rows 40.. of the trace, 4 stamps per 32-column sub-tile
+// (compiled in only with -DPA_TRACE_CHUNKS: the four clock reads per sub-tile cost the stand-alone GEMM 12 %)
+__device__ __forceinline__ void trace_chunk(const GemmParams& p, int tile_seq, int chunk, int slot) {
+#ifdef PA_TRACE_CHUNKS
+  if (p.trace != nullptr && blockIdx.x == 0 && tile_seq == 2 && chunk < 8) p.trace[320 + chunk * 4 + slot] = clock64();
+#endif
 }
 
 constexpr int GEMM_BLOCK_M = 128;
@@ -68,7 +75,8 @@ struct GemmCfg {
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int set = 0) { asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync_all() { asm volatile("bar.sync 3, 256;" ::: "memory"); }   // both epilogue sets
 
 // Tile sequence of one persistent worker (a CTA, or a cluster).  Classic: tiles `first, first+stride, ...` of fixed width.
 // Balanced: the (m-group, 64-column unit) grid is cut into equal contiguous ranges, one per worker, and each range is walked
@@ -122,7 +130,7 @@ struct TileWalk {
 //   full[stage]   leader's barrier, expect_tx = bytes of BOTH CTAs (every TMA load signals the leader's barrier)
 //   empty[stage]  each CTA's own barrier, released by the leader's multicast tcgen05.commit
 //   tfull[acc]    each CTA's own barrier (multicast commit);  tempty[acc]: leader's, 8 arrivals (4 epilogue warps x 2 CTAs)
-template <int STAGES, int CLUSTER, bool PAIR>
+template <int STAGES, int CLUSTER, bool PAIR, int ESETS = 1>
 __device__ __forceinline__ void gemm_init_barriers(uint64_t* bars) {      // one thread; bars: [2*STAGES + 4] mbarriers
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -134,7 +142,7 @@ __device__ __forceinline__ void gemm_init_barriers(uint64_t* bars) {      // one
   }
   for (int i = 0; i < 2; ++i) {
     mbar_init(&tfull_bar[i], 1);
-    mbar_init(&tempty_bar[i], PAIR ? 8 : 4);
+    mbar_init(&tempty_bar[i], (PAIR ? 8 : 4) * ESETS);
   }
 }
 
@@ -142,7 +150,9 @@ __device__ __forceinline__ void gemm_init_barriers(uint64_t* bars) {      // one
 // Barriers must be initialised and visible (cluster-wide when CLUSTER > 1) and TMEM allocated before the call.
 // LEAN: compile out the rarely used epilogue variants (row bias, residual, unaligned-output fallback) -- the fused kernels
 // run 20 warps per CTA and have only 96 registers per thread.
-template <int BLOCK_N, int STAGES, int CLUSTER, bool PAIR, bool LEAN = false>
+// ESETS: 1 = warps 4-7 drain the accumulator; 2 = warps 8-11 join and the two sets take alternate 32-column sub-tiles (each
+// set has its own staging region, named barrier and bulk-store groups; both sets publish to signal_ctr).
+template <int BLOCK_N, int STAGES, int CLUSTER, bool PAIR, bool LEAN = false, int ESETS = 1>
 __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                                          const GemmParams& p, uint8_t* smem, uint64_t* bars, uint32_t tmem_base) {
   static_assert(!PAIR || CLUSTER == 2, "cta_group::2 needs a cluster of exactly two CTAs");
@@ -157,7 +167,7 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
   const int num_kb = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   const int crank = (CLUSTER > 1) ? (int)cluster_ctarank() : 0;
   const int ncl = gridDim.x / CLUSTER;
-  const int cid = p.reverse_workers ? ncl - 1 - (int)(blockIdx.x / CLUSTER) : (int)(blockIdx.x / CLUSTER);   // persistent worker index
+  const int cid = ((int)(blockIdx.x / CLUSTER) + p.worker_shift) % ncl;   // persistent worker index
   constexpr uint16_t CMASK = (uint16_t)((1u << CLUSTER) - 1);
   constexpr int B_SLICE_ROWS = BLOCK_N / CLUSTER;
 
@@ -257,14 +267,20 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== epilogue (warps 4-7; wider CTAs of the fused kernels leave the rest idle here) ==========
+  } else if (warp >= 4 && warp < 4 + 4 * ESETS) {
+    // ===================== epilogue (warps 4-7 [+ 8-11]; wider CTAs of the fused kernels leave the rest idle here) ==
+    static_assert(ESETS == 1 || LEAN, "two epilogue sets only on the staged-store path");
+    const int eset = (warp - 4) >> 2;       // which set of four warps
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int trow = q * 32 + lane;         // row inside the tile
-    const bool leader = (warp == 4 && lane == 0);
+    const bool leader = (q == 0 && lane == 0);          // one per set: issues and tracks the set's bulk stores
+    const bool tracer = (warp == 4 && lane == 0);
     const int elt = (p.out_dtype == 2) ? 4 : 2;
     const int row_bytes = 32 * elt;         // staged sub-tile row: 128 B (fp32, SW128) or 64 B (16-bit, SW64)
-    uint8_t* cbuf = smem + Cfg::C_OFFSET;
+    uint8_t* cbuf = smem + Cfg::C_OFFSET + (ESETS == 2 ? eset * GEMM_CSTAGE_BYTES : 0);
+    // two sets: one 16 KB region each -- double-buffered for 16-bit output (8 KB sub-tiles), single for fp32
+    const int cbuf_stride = (ESETS == 2) ? GEMM_CSTAGE_BYTES / 2 : GEMM_CSTAGE_BYTES;
+    const bool single_buf = (ESETS == 2) && elt == 4;
     int acc = 0, cb = 0, tseq = 0;
     uint32_t acc_phase = 0;
     int pending_mt = -1;                     // fused kernels: tile whose stores are in flight and not yet published
@@ -280,7 +296,7 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
         if (pending_mt < p.m_tiles) signal_counter(p.signal_ctr + pending_mt);   // its stores were issued a whole mainloop ago
       }
       pending_mt = mt;
-      if (leader) trace_stamp(p, tseq, 4);
+      if (tracer) trace_stamp(p, tseq, 4);
       const uint32_t t_base = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
       const bool row_ok = row < p.M;
       const float bias_m = (!LEAN && p.bias_mode == 2 && row_ok) ? p.bias[row] : 0.f;
@@ -289,17 +305,22 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
       if (p.bias_mode == 1) {
         // column biases of this tile: one coalesced load into smem, then broadcast reads (was 32 scalar LDGs per chunk)
         const int et = threadIdx.x - 128;
-        for (int i = et; i < tw.ncols; i += 128) sbias[i] = (col0 + i < p.N) ? __ldg(p.bias + col0 + i) : 0.f;
-        epi_bar_sync();
+        if (ESETS == 2) epi_bar_sync_all();                // the other set has finished reading the previous tile's biases
+        if (et < 128)
+          for (int i = et; i < tw.ncols; i += 128) sbias[i] = (col0 + i < p.N) ? __ldg(p.bias + col0 + i) : 0.f;
+        if (ESETS == 2) epi_bar_sync_all();
+        else epi_bar_sync();
       }
 #pragma unroll 1
-      for (int c = 0; c < tw.ncols; c += 32) {
+      for (int c = eset * 32; c < tw.ncols; c += 32 * ESETS) {
         const int col = col0 + c;
         if (col >= p.N) break;              // uniform over the epilogue warps
         if (p.debug_flags & 1) break;       // experiment: no epilogue work at all (output garbage)
         uint32_t v[32];
+        if (tracer) trace_chunk(p, tseq, c >> 5, 0);
         tmem_ld32(t_base + c, v);
         tmem_ld_wait();
+        if (tracer) trace_chunk(p, tseq, c >> 5, 1);
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + bias_m;
@@ -345,9 +366,13 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
         }
         if (LEAN || p.tma_store) {
           // ---- staged path: this 128 x 32 sub-tile -> swizzled smem -> one TMA store
-          uint8_t* buf = cbuf + cb * GEMM_CSTAGE_BYTES;
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer cb's previous store has been read
-          epi_bar_sync();
+          uint8_t* buf = cbuf + (single_buf ? 0 : cb * cbuf_stride);
+          if (leader) {                                    // buffer cb's previous store has been read
+            if (single_buf) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          }
+          epi_bar_sync(eset);
+          if (tracer) trace_chunk(p, tseq, c >> 5, 2);
           uint8_t* rowp = buf + trow * row_bytes;
           if (p.out_dtype == 2) {
 #pragma unroll
@@ -368,7 +393,8 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
             }
           }
           fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA (async proxy)
-          epi_bar_sync();
+          epi_bar_sync(eset);
+          if (tracer) trace_chunk(p, tseq, c >> 5, 3);
           if (leader) {
             asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                              reinterpret_cast<uint64_t>(&tmD)),
@@ -401,7 +427,7 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
       if (p.bias_mode == 1 && !p.tma_store) epi_bar_sync();   // nobody may refill the bias buffer while it is being read
       tc_fence_before();
       __syncwarp();
-      if (leader) trace_stamp(p, tseq, 5);
+      if (tracer) trace_stamp(p, tseq, 5);
       if (lane == 0) {
         if (PAIR) mbar_arrive_leader(&tempty_bar[acc]);
         else mbar_arrive(&tempty_bar[acc]);

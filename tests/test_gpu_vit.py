@@ -125,14 +125,17 @@ def test_swap_into_reference_shaped_block():
 
 @pytest.mark.parametrize("B,C,H,N", [(64, 768, 12, 197), (5, 128, 2, 197), (3, 256, 4, 64), (16, 1024, 16, 197)])
 def test_vit_fused_single_launch_matches_three_launch_path(B, C, H, N, monkeypatch):
-    """PA_VIT_FUSED=1: the whole forward as ONE launch (phases chained by dependency counters).  Same arithmetic in the
+    """The default path: the whole forward as ONE launch (phases chained by dependency counters).  Same arithmetic in the
     same order as the three-launch path -> bit-identical output; repeated runs stay identical (no race)."""
     from pytorch_attention_b200 import _lib
     m, x = _fresh(C, H, B, N, 11, qkv_bias=(C == 128))
     m = m.cuda()
     xg = x.cuda()
     with torch.no_grad():
+        monkeypatch.setenv("PA_VIT_FUSED", "0")
+        n0 = _lib.launch_count()
         y3 = m(xg)
+        assert _lib.launch_count() - n0 == 3
         monkeypatch.setenv("PA_VIT_FUSED", "1")
         n0 = _lib.launch_count()
         y1 = m(xg)

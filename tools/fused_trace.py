@@ -1,4 +1,4 @@
-"""Phase timeline of CTA 0 of the fused single-launch ViT kernel (clock64 stamps, PA_VIT_FUSED=1)."""
+"""Phase timeline of CTA 0 of the fused single-launch ViT kernel (clock64 stamps per tile/item, globaltimer per phase)."""
 import sys, os, ctypes
 os.environ["PA_VIT_FUSED"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -24,7 +24,13 @@ def rel(v): return int(v) - t0 if int(v) else None
 print("phase 1 (qkv GEMM) tiles: mma_start / epi_done")
 for i in range(64):
     if int(g1[i, 1]) == 0: break
-    print(f"  tile {i}: mma_start {rel(g1[i,1])}  first_full {rel(g1[i,2])}  mma_issued {rel(g1[i,3])}  epi_done {rel(g1[i,5])}")
+    print(f"  tile {i}: mma_start {rel(g1[i,1])}  first_full {rel(g1[i,2])}  mma_issued {rel(g1[i,3])}  epi_ready {rel(g1[i,4])}  epi_done {rel(g1[i,5])}")
+ck = g1.reshape(-1)[320:352].view(8, 4)
+print("phase 1 epilogue of tile 2, per 32-column sub-tile (warp 4 lane 0): loop_top  tmem_ld_done  staging_free(bar1)  staged(bar2)")
+for c in range(8):
+    if int(ck[c, 0]) == 0: continue
+    a, b, c2, d = [int(x) - t0 for x in ck[c]]
+    print(f"   chunk {c}: {a:8d}  ld +{b-a:4d}  bar1 +{c2-b:4d}  store+fence+bar2 +{d-c2:4d}")
 print("phase 2 (attention) items: q_ok / S0_iss / w0 done / w1 done")
 for i in range(32):
     if int(at[i, 1]) == 0: break

@@ -25,6 +25,12 @@ for (M, N, K, bn, cl) in [(12608, 2304, 768, 256, 1), (12608, 2304, 768, 256, -2
             break
         r = [int(t[i, s]) - t0 for s in (6, 1, 2, 3, 4, 5)]
         print(f"{i:4d}  {r[0]:10d} {r[1]:10d} {r[2]:11d} {r[3]:11d} {r[4]:11d} {r[5]:9d}   | {r[3]-r[1]:8d} {r[5]-r[4]:9d}")
+    ck = t.reshape(-1)[320:352].view(8, 4)
+    print("epilogue of tile 2, per 32-column sub-tile (warp 4 lane 0): loop_top  tmem_ld_done  staging_free(bar1)  staged(bar2)")
+    for c in range(8):
+        if int(ck[c, 0]) == 0: continue
+        a, b, c2, d = [int(x) - t0 for x in ck[c]]
+        print(f"   chunk {c}: {a:8d}  ld +{b-a:4d}  bar1 +{c2-b:4d}  store+fence+bar2 +{d-c2:4d}")
     kt = t[32:40].reshape(-1)[:64].view(16, 4)
     print("MMA thread, tile 2, per k-block: before_wait  after_wait  after_4_mma_issue  after_commit   (deltas vs previous k-block's after_commit)")
     prev = None
