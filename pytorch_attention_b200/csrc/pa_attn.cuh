@@ -124,14 +124,31 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[N], uint32_t (&pk
   return s0 + s1;
 }
 
+// exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], max rel. error 7.6e-5 -- below the fp16
+// rounding of P): the MUFU unit (16 ex2 / clk / SM) is the limiter of pass 2, so a fraction of each step's exponentials
+// is computed here instead.  x <= 0 up to rounding; clamped so the result stays a normal number (2^-125 ~ 0).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;          // 1.5 * 2^23: the nearest integer n lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);    // [-0.5, 0.5]
+  float q = fmaf(0.0551695712f, f, 0.242606208f);
+  q = fmaf(q, f, 0.693260908f);
+  q = fmaf(q, f, 0.999928415f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));   // * 2^n
+}
+
 // Stage A of the skewed pass 2: e = exp2(s * sl2 - mxs) for the first nval columns of a 16-column step (0 beyond)
 __device__ __forceinline__ void exp_stage(const uint32_t (&v)[16], float (&e)[16], int nval, float sl2, float mxs, int dbg = 0) {
   if (dbg & 1) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) e[i] = fmaf(__uint_as_float(v[i]), sl2, -mxs);
   } else if (nval >= 16) {
+    // 4 of 16 on the FMA pipe (measured: 4 -> -5 %, 6 and 8 of 16 -> no gain: the FMA pipe / issue slots fill up)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) e[i] = ex2f(fmaf(__uint_as_float(v[i]), sl2, -mxs));
+    for (int i = 0; i < 16; ++i) {
+      const float x = fmaf(__uint_as_float(v[i]), sl2, -mxs);
+      e[i] = ((i & 3) == 3) ? ex2_poly(x) : ex2f(x);
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -407,7 +424,13 @@ __device__ __forceinline__ void attn_run(const CUtensorMap& tmQ, const CUtensorM
         if (warp_active) {
           int k = (p.debug_flags & 4) ? nst : 0;
 #pragma unroll 1
-          for (; k < nst; ++k) {
+          for (; k + 1 < nst; k += 2) {        // 32 columns per TMEM round trip (only the max is kept: registers are free here)
+            uint32_t v[32];
+            tmem_ld32(t_my + k * 16, v);
+            tmem_ld_wait();
+            mx = chunk_max<32>(v, nvalid - k * 16, mx);
+          }
+          if (k < nst) {
             uint32_t v[16];
             tmem_ld16(t_my + k * 16, v);
             tmem_ld_wait();
@@ -443,6 +466,7 @@ __device__ __forceinline__ void attn_run(const CUtensorMap& tmQ, const CUtensorM
           uint32_t va[16], pk[8];
           float e[16];
           float s0 = 0.f, s1 = 0.f;
+          // (prefetching step k+1's TMEM load into a second register buffer was measured twice: 39 -> 52 us)
 #pragma unroll 1
           for (int k = 0; k < nst; ++k) {      // four softmax warps per scheduler hide the TMEM / MUFU latencies of each other
             tmem_ld16(t_my + k * 16, va);
