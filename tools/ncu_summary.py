@@ -36,7 +36,7 @@ def main(rep, launches_csv, tag):
             return 0.0
         tot = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
         lines.append(f"- dram bytes read+write per launch = {tot / 1e6:.2f} MB")
-        key = "attn" if "attn_core" in r[ki] else "gemm"
+        key = "fused" if "vit_fused" in r[ki] else "attn" if "attn_core" in r[ki] else "gemm"
         traffic.setdefault(key, []).append(tot)
         lines.append("")
     # launch list shares
@@ -54,12 +54,22 @@ def main(rep, launches_csv, tag):
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         lines.append(f"| `{k}` | {len(v)} | {sum(v) / len(v) / 1000:.2f} | {sum(v) / tot * 100:.1f}% |")
     open(f"profiles/ncu_summary_{tag}.md", "w").write("\n".join(lines) + "\n")
-    gemm = traffic.get("gemm", [])
-    json.dump({"qkv_gemm_dram_bytes_per_launch": gemm[0] if gemm else None,
-               "attn_core_dram_bytes_per_launch": (traffic.get("attn") or [None])[0],
-               "source": f"profiles/ncu_summary_{tag}.md"}, open("profiles/traffic.json", "w"), indent=1)
-    print("\n".join(lines))
+    # merge into traffic.json (bench.py reads the per-launch DRAM bytes of its dominant kernel from here)
+    try:
+        tj = json.load(open("profiles/traffic.json"))
+    except Exception:
+        tj = {}
+    if traffic.get("gemm"):
+        tj["qkv_gemm_dram_bytes_per_launch"] = traffic["gemm"][0]
+    if traffic.get("attn"):
+        tj["attn_core_dram_bytes_per_launch"] = traffic["attn"][0]
+    if traffic.get("fused"):
+        tj["vit_fused_dram_bytes_per_launch"] = traffic["fused"][0]
+        tj["vit_fused_source"] = f"profiles/ncu_summary_{tag}.md"
+    else:
+        tj["source"] = f"profiles/ncu_summary_{tag}.md"
+    json.dump(tj, open("profiles/traffic.json", "w"), indent=1)
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:4])
+    main(sys.argv[1], sys.argv[2], sys.argv[3])
