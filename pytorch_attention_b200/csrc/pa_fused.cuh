@@ -24,7 +24,7 @@ struct VitFusedParams {
 };
 
 constexpr int FUSED_BN1 = 256, FUSED_ST1 = 6;   // qkv: 256 x 256 pair tiles
-constexpr int FUSED_ESETS = 2;                   // GEMM phases drain accumulators with warps 4-11 (the CTA has 20 warps anyway)
+constexpr int FUSED_ESETS = 4;                   // GEMM phases drain accumulators with warps 4-19 (all softmax warps of the attention phase)
 constexpr int FUSED_BN2 = 192, FUSED_ST2 = 5;   // proj: 256 x 192 pair tiles
 
 __host__ __device__ inline int vit_fused_data_bytes(int kb) {

@@ -76,7 +76,8 @@ struct GemmCfg {
 };
 
 __device__ __forceinline__ void epi_bar_sync(int set = 0) { asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory"); }
-__device__ __forceinline__ void epi_bar_sync_all() { asm volatile("bar.sync 3, 256;" ::: "memory"); }   // both epilogue sets
+template <int ESETS>
+__device__ __forceinline__ void epi_bar_sync_all() { asm volatile("bar.sync 5, %0;" ::"n"(128 * ESETS) : "memory"); }   // all epilogue sets
 
 // Tile sequence of one persistent worker (a CTA, or a cluster).  Classic: tiles `first, first+stride, ...` of fixed width.
 // Balanced: the (m-group, 64-column unit) grid is cut into equal contiguous ranges, one per worker, and each range is walked
@@ -150,7 +151,7 @@ __device__ __forceinline__ void gemm_init_barriers(uint64_t* bars) {      // one
 // Barriers must be initialised and visible (cluster-wide when CLUSTER > 1) and TMEM allocated before the call.
 // LEAN: compile out the rarely used epilogue variants (row bias, residual, unaligned-output fallback) -- the fused kernels
 // run 20 warps per CTA and have only 96 registers per thread.
-// ESETS: 1 = warps 4-7 drain the accumulator; 2 = warps 8-11 join and the two sets take alternate 32-column sub-tiles (each
+// ESETS: 1 = warps 4-7 drain the accumulator; 2 / 4 = warps 8-11 / 8-19 join and the sets take the 32-column sub-tiles round-robin (each
 // set has its own staging region, named barrier and bulk-store groups; both sets publish to signal_ctr).
 template <int BLOCK_N, int STAGES, int CLUSTER, bool PAIR, bool LEAN = false, int ESETS = 1>
 __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
@@ -269,7 +270,8 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
     }
   } else if (warp >= 4 && warp < 4 + 4 * ESETS) {
     // ===================== epilogue (warps 4-7 [+ 8-11]; wider CTAs of the fused kernels leave the rest idle here) ==
-    static_assert(ESETS == 1 || LEAN, "two epilogue sets only on the staged-store path");
+    static_assert(ESETS == 1 || LEAN, "several epilogue sets only on the staged-store path");
+    static_assert(ESETS == 1 || ESETS == 2 || ESETS == 4, "1, 2 or 4 epilogue sets");
     const int eset = (warp - 4) >> 2;       // which set of four warps
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int trow = q * 32 + lane;         // row inside the tile
@@ -277,10 +279,13 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
     const bool tracer = (warp == 4 && lane == 0);
     const int elt = (p.out_dtype == 2) ? 4 : 2;
     const int row_bytes = 32 * elt;         // staged sub-tile row: 128 B (fp32, SW128) or 64 B (16-bit, SW64)
-    uint8_t* cbuf = smem + Cfg::C_OFFSET + (ESETS == 2 ? eset * GEMM_CSTAGE_BYTES : 0);
-    // two sets: one 16 KB region each -- double-buffered for 16-bit output (8 KB sub-tiles), single for fp32
-    const int cbuf_stride = (ESETS == 2) ? GEMM_CSTAGE_BYTES / 2 : GEMM_CSTAGE_BYTES;
-    const bool single_buf = (ESETS == 2) && elt == 4;
+    // the 32 KB staging area is split between the ACTIVE sets; a sub-tile is 8 KB (16-bit) or 16 KB (fp32), so with four sets
+    // an fp32 output leaves sets 2-3 idle (they still take part in every barrier / arrival / publication)
+    const int active_sets = (ESETS == 4 && elt == 4) ? 2 : ESETS;
+    const int region = 2 * GEMM_CSTAGE_BYTES / active_sets;
+    const int cbuf_stride = (ESETS == 1) ? GEMM_CSTAGE_BYTES : 128 * row_bytes;
+    const bool single_buf = (ESETS > 1) && region < 2 * 128 * row_bytes;
+    uint8_t* cbuf = smem + Cfg::C_OFFSET + (eset < active_sets ? eset : 0) * region;
     int acc = 0, cb = 0, tseq = 0;
     uint32_t acc_phase = 0;
     int pending_mt = -1;                     // fused kernels: tile whose stores are in flight and not yet published
@@ -305,14 +310,14 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
       if (p.bias_mode == 1) {
         // column biases of this tile: one coalesced load into smem, then broadcast reads (was 32 scalar LDGs per chunk)
         const int et = threadIdx.x - 128;
-        if (ESETS == 2) epi_bar_sync_all();                // the other set has finished reading the previous tile's biases
+        if (ESETS > 1) epi_bar_sync_all<ESETS>();          // the other sets have finished reading the previous tile's biases
         if (et < 128)
           for (int i = et; i < tw.ncols; i += 128) sbias[i] = (col0 + i < p.N) ? __ldg(p.bias + col0 + i) : 0.f;
-        if (ESETS == 2) epi_bar_sync_all();
+        if (ESETS > 1) epi_bar_sync_all<ESETS>();
         else epi_bar_sync();
       }
 #pragma unroll 1
-      for (int c = eset * 32; c < tw.ncols; c += 32 * ESETS) {
+      for (int c = (eset < active_sets ? eset * 32 : tw.ncols); c < tw.ncols; c += 32 * active_sets) {
         const int col = col0 + c;
         if (col >= p.N) break;              // uniform over the epilogue warps
         if (p.debug_flags & 1) break;       // experiment: no epilogue work at all (output garbage)

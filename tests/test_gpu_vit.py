@@ -123,13 +123,15 @@ def test_swap_into_reference_shaped_block():
     m.load_state_dict(ref_like.state_dict())
 
 
-@pytest.mark.parametrize("B,C,H,N", [(64, 768, 12, 197), (5, 128, 2, 197), (3, 256, 4, 64), (16, 1024, 16, 197)])
+@pytest.mark.parametrize("B,C,H,N", [(64, 768, 12, 197), (5, 128, 2, 197), (3, 256, 4, 64), (16, 1024, 16, 197), (7, 384, 6, 200)])
 def test_vit_fused_single_launch_matches_three_launch_path(B, C, H, N, monkeypatch):
     """The default path: the whole forward as ONE launch (phases chained by dependency counters).  Same arithmetic in the
     same order as the three-launch path -> bit-identical output; repeated runs stay identical (no race)."""
     from pytorch_attention_b200 import _lib
     m, x = _fresh(C, H, B, N, 11, qkv_bias=(C == 128))
     m = m.cuda()
+    if C == 384:
+        m.out_dtype = torch.float32        # fp32 y: the staging area holds fewer sub-tiles, two of the four epilogue sets idle
     xg = x.cuda()
     with torch.no_grad():
         monkeypatch.setenv("PA_VIT_FUSED", "0")
