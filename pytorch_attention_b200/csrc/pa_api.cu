@@ -381,6 +381,48 @@ int grid_for(long long work_items, int threads) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ exports
+// tile width of a GEMM phase of the fused kernel: the cost model of pick_block_n restricted to the instantiated widths
+static int fused_pick_bn(int M, int N, int K) {
+  const int workers = num_sms() / 2, m_tiles = (M + 255) / 256, num_kb = (K + 63) / 64;
+  double best = 1e30;
+  int best_bn = 256;
+  const int cands[2] = {256, 192};
+  for (int i = 0; i < 2; ++i) {
+    const int bn = cands[i];
+    const long long tiles = (long long)m_tiles * ((N + bn - 1) / bn);
+    // inside the fused kernel a partial last wave is mostly absorbed by the next phase: charge the exact average plus
+    // half a tile for the remainder instead of whole waves
+    const double per_tile = 2.0 * num_kb * bn + 700.0;
+    const double cost = ((double)tiles / workers + (tiles % workers ? 0.5 : 0.0)) * per_tile;
+    if (cost < best * 0.999) { best = cost; best_bn = bn; }
+  }
+  return best_bn;
+}
+
+template <int BN1, int BN2>
+static int launch_vit_fused(const GemmPlan& p1, const AttnPlan& pa_, const GemmPlan& p2, const VitFusedParams& fp, int smem, cudaStream_t st) {
+  static int attr_done[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_done[dev & 63] < smem) {
+    PA_CUDA_OK(cudaFuncSetAttribute(vit_fused_kernel<BN1, BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done[dev & 63] = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((num_sms() / 2) * 2);
+  cfg.blockDim = dim3(ATTN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  PA_CUDA_OK(cudaLaunchKernelEx(&cfg, vit_fused_kernel<BN1, BN2>, p1.tmA, p1.tmB, p1.tmD, pa_.tq, pa_.tk, pa_.tv, pa_.to, p2.tmA, p2.tmB,
+                                p2.tmD, fp));
+  return PA_OK;
+}
+
+
 extern "C" {
 
 int pa_version(void) { return PA_VERSION; }
@@ -449,7 +491,8 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
     g1.A = a->x; g1.lda = C; g1.B = a->qkv_weight; g1.ldb = C; g1.D = qkv; g1.ldd = 3 * C;
     g1.bias = a->qkv_bias; g1.bias_mode = a->qkv_bias ? 1 : 0;
     GemmPlan p1;
-    if ((rc = gemm_prepare(&g1, &p1, FUSED_BN1, -2))) return rc;
+    const int bn1 = fused_pick_bn((int)rows, 3 * C, C), bn2 = fused_pick_bn((int)rows, C, C);
+    if ((rc = gemm_prepare(&g1, &p1, bn1, -2))) return rc;
     AttnLaunch al = {};
     al.hd = 64; al.G = a->B; al.H = a->H; al.n_q = a->N; al.n_k = a->N;
     al.q = qkv; al.ldq = 3 * C; al.q_group = (long long)a->N * 3 * C; al.q_col0 = 0;
@@ -468,8 +511,9 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
     g2.A = obuf; g2.lda = C; g2.B = a->proj_weight; g2.ldb = C; g2.D = a->y; g2.ldd = C;
     g2.bias = a->proj_bias; g2.bias_mode = a->proj_bias ? 1 : 0;
     GemmPlan p2;
-    if ((rc = gemm_prepare(&g2, &p2, FUSED_BN2, -2))) return rc;
-    const int smem = vit_fused_smem_bytes(pa_.p.kb);
+    if ((rc = gemm_prepare(&g2, &p2, bn2, -2))) return rc;
+    const int smem = bn1 == 256 ? (bn2 == 256 ? vit_fused_smem_bytes<256, 256>(pa_.p.kb) : vit_fused_smem_bytes<256, 192>(pa_.p.kb))
+                                : (bn2 == 256 ? vit_fused_smem_bytes<192, 256>(pa_.p.kb) : vit_fused_smem_bytes<192, 192>(pa_.p.kb));
     if (!p1.p.tma_store || !p2.p.tma_store || smem > 227 * 1024) {
       if (fused_forced) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(fused): outputs must be TMA-storable and the plan (%d B) must fit", smem);
       fused_ok = false;
@@ -496,24 +540,11 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
     fp.at.wait_rows_per_group = a->N;
     fp.at.signal_ctr = counters + n_mt;                            // per image
     fp.g2.wait_ctr = counters + n_mt; fp.g2.wait_rows = a->N; fp.g2.wait_target = a->H * fp.at.q_tiles;
-    static int attr_done[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (attr_done[dev & 63] < smem) {
-      PA_CUDA_OK(cudaFuncSetAttribute(vit_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_done[dev & 63] = smem;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((num_sms() / 2) * 2);
-    cfg.blockDim = dim3(ATTN_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    PA_CUDA_OK(cudaLaunchKernelEx(&cfg, vit_fused_kernel, p1.tmA, p1.tmB, p1.tmD, pa_.tq, pa_.tk, pa_.tv, pa_.to, p2.tmA, p2.tmB,
-                                  p2.tmD, fp));
+    if (bn1 == 256 && bn2 == 192) rc = launch_vit_fused<256, 192>(p1, pa_, p2, fp, smem, st);
+    else if (bn1 == 256) rc = launch_vit_fused<256, 256>(p1, pa_, p2, fp, smem, st);
+    else if (bn2 == 256) rc = launch_vit_fused<192, 256>(p1, pa_, p2, fp, smem, st);
+    else rc = launch_vit_fused<192, 192>(p1, pa_, p2, fp, smem, st);
+    if (rc) return rc;
     launch_counter()++;
     return PA_OK;
     }

@@ -23,21 +23,25 @@ struct VitFusedParams {
   GemmParams g2;     // output projection
 };
 
-constexpr int FUSED_BN1 = 256, FUSED_ST1 = 6;   // qkv: 256 x 256 pair tiles
 constexpr int FUSED_ESETS = 4;                   // GEMM phases drain accumulators with warps 4-19 (all softmax warps of the attention phase)
-constexpr int FUSED_BN2 = 192, FUSED_ST2 = 5;   // proj: 256 x 192 pair tiles
+// GEMM phases use 256 x BN pair tiles, BN in {192, 256} chosen per phase by the host's tile cost model (e.g. ViT-B: qkv 256,
+// proj 192; ViT-L: qkv 192, proj 256 -- 1024 output columns are 5.33 tiles of 192)
+__host__ __device__ constexpr int fused_stages(int bn) { return bn == 256 ? 6 : 5; }
 
+template <int BN1, int BN2>
 __host__ __device__ inline int vit_fused_data_bytes(int kb) {
-  const int g1 = GemmCfg<FUSED_BN1, FUSED_ST1, true>::BAR_OFFSET;
-  const int g2 = GemmCfg<FUSED_BN2, FUSED_ST2, true>::BAR_OFFSET;
+  const int g1 = GemmCfg<BN1, fused_stages(BN1), true>::BAR_OFFSET;
+  const int g2 = GemmCfg<BN2, fused_stages(BN2), true>::BAR_OFFSET;
   const int at = 2 * 256 * 128 + 4 * kb * 128 + attn_ostage_bytes(64, true);
   int m = g1 > g2 ? g1 : g2;
   return m > at ? m : at;
 }
+template <int BN1, int BN2>
 __host__ __device__ inline int vit_fused_smem_bytes(int kb) {
-  return vit_fused_data_bytes(kb) + (2 * FUSED_ST1 + 4 + 16 + 2 * FUSED_ST2 + 4) * 8 + 16 + 1024;
+  return vit_fused_data_bytes<BN1, BN2>(kb) + (2 * fused_stages(BN1) + 4 + 16 + 2 * fused_stages(BN2) + 4) * 8 + 16 + 1024;
 }
 
+template <int BN1, int BN2>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 vit_fused_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmD1, const __grid_constant__ CUtensorMap tmQ,
@@ -45,9 +49,10 @@ vit_fused_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD2,
                  const VitFusedParams P) {
+  constexpr int FUSED_BN1 = BN1, FUSED_ST1 = fused_stages(BN1), FUSED_BN2 = BN2, FUSED_ST2 = fused_stages(BN2);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars1 = reinterpret_cast<uint64_t*>(smem + vit_fused_data_bytes(P.at.kb));
+  uint64_t* bars1 = reinterpret_cast<uint64_t*>(smem + vit_fused_data_bytes<BN1, BN2>(P.at.kb));
   uint64_t* barsA = bars1 + (2 * FUSED_ST1 + 4);
   uint64_t* bars2 = barsA + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars2 + (2 * FUSED_ST2 + 4));
