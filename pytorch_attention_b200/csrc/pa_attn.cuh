@@ -293,6 +293,31 @@ __device__ __forceinline__ void attn_run(const CUtensorMap& tmQ, const CUtensorM
       }
       umma_commit(&o_full[s]);
     };
+    // S = Q K^T of a slot is issued in two parts.  The columns below the O accumulator ([0, 256-HD)) hold nothing the
+    // previous item still needs once its PV MMA has been ISSUED (the tensor pipe executes in issue order, and the softmax
+    // warps finished with S/P before p_full), so that part goes out BEFORE the wait for the slot hand-back and runs under
+    // the previous item's O read-out; only the columns that overlap O (16 of ViT's 208) wait for slot_empty.
+    const int s_n1 = p.kb < Cfg::O_COL ? p.kb : Cfg::O_COL;
+    const uint32_t idesc_s1 = (p.idesc_s & ~(0x3Fu << 17)) | ((uint32_t)(s_n1 >> 3) << 17);
+    const uint32_t idesc_s2 = (p.idesc_s & ~(0x3Fu << 17)) | ((uint32_t)((p.kb - s_n1) >> 3) << 17);
+    const uint64_t k_off2 = (uint64_t)((s_n1 * Cfg::ROW_BYTES) >> 4);        // K rows s_n1.. (whole swizzle atoms)
+    auto issue_s_early = [&](uint32_t d_tmem, uint64_t qdesc, uint64_t kdesc) {
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_ss(d_tmem, qdesc + 2 * k, kdesc + 2 * k, idesc_s1, k != 0);
+      }
+      __syncwarp();
+    };
+    auto issue_s_late = [&](uint32_t d_tmem, uint64_t qdesc, uint64_t kdesc, uint64_t* bar) {
+      if (elect_one()) {
+        if (p.kb > s_n1) {
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) umma_ss(d_tmem + s_n1, qdesc + 2 * k, kdesc + k_off2 + 2 * k, idesc_s2, k != 0);
+        }
+        umma_commit(bar);
+      }
+      __syncwarp();
+    };
     auto flush_pending = [&]() {
       if (!pend) return;
       mbar_wait(&p_full[1], pf_ph1);
@@ -322,39 +347,30 @@ __device__ __forceinline__ void attn_run(const CUtensorMap& tmQ, const CUtensorM
         const uint64_t kdesc = make_sdesc(kbuf, 16, Cfg::SBO, Cfg::SWZ);
         // ---- S of slot 0
         {
+          const int tile = WINDOWED ? (2 * pr) : 0;
+          const uint64_t qdesc = make_sdesc(qbuf + tile * Cfg::Q_TILE_BYTES, 16, Cfg::SBO, Cfg::SWZ);
+          issue_s_early(tmem_base, qdesc, kdesc);
           if (j == 0) {
             mbar_wait(&slot_empty[0], se_ph0 ^ 1);
             se_ph0 ^= 1;
             tc_fence_after();
           }
-          const int tile = WINDOWED ? (2 * pr) : 0;
-          const uint64_t qdesc = make_sdesc(qbuf + tile * Cfg::Q_TILE_BYTES, 16, Cfg::SBO, Cfg::SWZ);
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_base, qdesc + 2 * k, kdesc + 2 * k, p.idesc_s, k != 0);
-            umma_commit(&s_full[0]);
-          }
-          __syncwarp();
+          issue_s_late(tmem_base, qdesc, kdesc, &s_full[0]);
           if (lane == 0) ATTN_TRACE(iseq, 1);
         }
         // ---- PV of slot 1 from the previous step
         flush_pending();
         // ---- S of slot 1
         if (nslots == 2) {
+          const int tile = WINDOWED ? (2 * pr + 1) : 1;
+          const uint64_t qdesc = make_sdesc(qbuf + tile * Cfg::Q_TILE_BYTES, 16, Cfg::SBO, Cfg::SWZ);
+          issue_s_early(tmem_base + ATTN_SLOT_COLS, qdesc, kdesc);
           if (j == 0) {
             mbar_wait(&slot_empty[1], se_ph1 ^ 1);
             se_ph1 ^= 1;
             tc_fence_after();
           }
-          const int tile = WINDOWED ? (2 * pr + 1) : 1;
-          const uint64_t qdesc = make_sdesc(qbuf + tile * Cfg::Q_TILE_BYTES, 16, Cfg::SBO, Cfg::SWZ);
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k)
-              umma_ss(tmem_base + ATTN_SLOT_COLS, qdesc + 2 * k, kdesc + 2 * k, p.idesc_s, k != 0);
-            umma_commit(&s_full[1]);
-          }
-          __syncwarp();
+          issue_s_late(tmem_base + ATTN_SLOT_COLS, qdesc, kdesc, &s_full[1]);
           if (lane == 0) ATTN_TRACE(iseq, 2);
         }
         // ---- PV of slot 0
