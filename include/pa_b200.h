@@ -98,6 +98,13 @@ typedef struct {
   const float* proj_bias;    /* [C] fp32 or NULL */
   void* y;                   /* [B,N,C] */
 } pa_vit_args;
+/* One kernel launch when N <= 256 (qkv GEMM -> attention -> proj GEMM phases of a persistent kernel, ordered across SMs by
+ * dependency counters kept in the workspace, which the call zeroes with a cudaMemsetAsync on the same stream); three
+ * stream-ordered launches otherwise.  Both give bit-identical results.  Environment: PA_VIT_FUSED=0 forces the three
+ * launches, PA_VIT_FUSED=1 turns a shape the fused kernel cannot take into PA_ERR_UNSUPPORTED instead of switching.
+ * The fused kernel occupies every SM with one resident CTA and spin-waits between its phases: do not make another
+ * kernel that runs concurrently on the same device wait for this call (it would only be delayed, never deadlocked,
+ * by kernels that finish on their own). */
 size_t pa_vit_workspace_bytes(const pa_vit_args* a);
 int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -491,7 +491,9 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
     g1.A = a->x; g1.lda = C; g1.B = a->qkv_weight; g1.ldb = C; g1.D = qkv; g1.ldd = 3 * C;
     g1.bias = a->qkv_bias; g1.bias_mode = a->qkv_bias ? 1 : 0;
     GemmPlan p1;
-    const int bn1 = fused_pick_bn((int)rows, 3 * C, C), bn2 = fused_pick_bn((int)rows, C, C);
+    int bn1 = fused_pick_bn((int)rows, 3 * C, C), bn2 = fused_pick_bn((int)rows, C, C);
+    if (const char* e = getenv("PA_FUSED_BN1")) { const int v = atoi(e); if (v == 192 || v == 256) bn1 = v; }   // experiments
+    if (const char* e = getenv("PA_FUSED_BN2")) { const int v = atoi(e); if (v == 192 || v == 256) bn2 = v; }
     if ((rc = gemm_prepare(&g1, &p1, bn1, -2))) return rc;
     AttnLaunch al = {};
     al.hd = 64; al.G = a->B; al.H = a->H; al.n_q = a->N; al.n_k = a->N;
