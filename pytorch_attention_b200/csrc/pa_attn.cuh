@@ -482,9 +482,12 @@ __device__ __forceinline__ void attn_run(const CUtensorMap& tmQ, const CUtensorM
           uint32_t va[16], pk[8];
           float e[16];
           float s0 = 0.f, s1 = 0.f;
-          // (prefetching step k+1's TMEM load into a second register buffer was measured twice: 39 -> 52 us)
+          // Every attempt to have the next step's TMEM load in flight while this step computes was slower on B200: a second
+          // register buffer (39 -> 52 us, twice) and also re-using `va` as soon as the exponent arguments are formed, with
+          // no extra registers (35 -> 47 us).  A tcgen05.ld overlapping this warp's tcgen05.st / MUFU stream loses more than
+          // the latency it hides; the other three softmax warps of the scheduler are what covers it.
 #pragma unroll 1
-          for (int k = 0; k < nst; ++k) {      // four softmax warps per scheduler hide the TMEM / MUFU latencies of each other
+          for (int k = 0; k < nst; ++k) {
             tmem_ld16(t_my + k * 16, va);
             tmem_ld_wait();
             exp_stage(va, e, nvalid - k * 16, sl2, mxs, p.debug_flags);
