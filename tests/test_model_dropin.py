@@ -1,0 +1,78 @@
+"""The drop-in attention inside a WHOLE reference model (SURVEY.md §8b "what calls it").
+
+tests/golden/models/vit_tiny.npz holds the parameters, an input batch and the logits of the real reference
+`ViT.VisionTransformer` (oracle/make_golden_model.py).  The model glue around the attention modules is restated in
+oracle/model_glue.py, so the same model can be evaluated where /root/reference is absent:
+  * CPU: glue + oracle attention reproduces the reference logits (pins the glue);
+  * CPU, reference mounted: the drop-in class substituted into the reference's own model constructs and loads the
+    reference state_dict strictly (constructor signature + keys), and refuses to run on CPU;
+  * GPU: glue + B200 drop-in attention (fp16 I/O) against the reference logits.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from _util import GOLDEN_DIR, rel_fro
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import vit_attention  # noqa: E402
+from oracle.model_glue import attention_state, vit_model_forward  # noqa: E402
+
+CFG = dict(image_size=64, patch_size=16, in_channels=3, depths=2, num_heads=2, embedding_dim=128, num_classes=10)
+REF = "/root/reference/vision_transformers"
+
+
+def _load():
+    z = np.load(os.path.join(GOLDEN_DIR, "models", "vit_tiny.npz"))
+    sd = {k[2:]: torch.from_numpy(z[k].astype(np.float32)) for k in z.files if k.startswith("p.")}
+    return sd, torch.from_numpy(z["in.x"].astype(np.float32)), torch.from_numpy(z["y_ref"])
+
+
+def test_glue_with_oracle_attention_reproduces_reference_model_logits():
+    sd, x, y_ref = _load()
+
+    def attn(i, t):
+        a = attention_state(sd, i)
+        return vit_attention(t, a["qkv.weight"], a.get("qkv.bias"), a["proj.weight"], a["proj.bias"], CFG["num_heads"])
+
+    y = vit_model_forward(sd, x, attn, CFG["patch_size"], CFG["depths"])
+    assert (y - y_ref).abs().max().item() <= 2e-5 * y_ref.abs().max().item()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted")
+def test_class_swap_inside_the_reference_model_constructs_and_loads(monkeypatch):
+    import pytorch_attention_b200 as pa
+    monkeypatch.syspath_prepend(REF)
+    import ViT
+    monkeypatch.setattr(ViT, "Attention", pa.vit.Attention)        # the substitution INTEGRATION.md describes
+    model = ViT.VisionTransformer(**CFG).eval()                    # ViT.py:98 constructs the drop-in with the reference's arguments
+    assert all(isinstance(b.attn, pa.vit.Attention) for b in model.blocks)
+    sd, x, _ = _load()
+    model.load_state_dict(sd, strict=True)                         # identical keys and shapes
+    with pytest.raises(RuntimeError, match="CPU"):                 # product path: no CPU fallback
+        with torch.no_grad():
+            model(x)
+
+
+@pytest.mark.gpu
+def test_dropin_attention_inside_the_whole_model_matches_reference_logits():
+    import pytorch_attention_b200 as pa
+    sd, x, y_ref = _load()
+    dev = torch.device("cuda", 0)
+    sdg = {k: v.to(dev) for k, v in sd.items()}
+    mods = []
+    for i in range(CFG["depths"]):
+        m = pa.vit.Attention(CFG["embedding_dim"], CFG["num_heads"]).eval()
+        m.load_state_dict(attention_state(sd, i), strict=True)
+        mods.append(m.to(dev))
+
+    def attn(i, t):
+        return mods[i](t.half()).float()                           # LayerNorm output rounded once to the kernel's fp16 input
+
+    with torch.no_grad():
+        y = vit_model_forward(sdg, x.to(dev), attn, CFG["patch_size"], CFG["depths"]).cpu()
+    # the path's own tolerance is 1e-3 per attention; two blocks, fp16-rounded attention inputs and the MLP/head amplify it
+    assert rel_fro(y, y_ref) < 3e-3, rel_fro(y, y_ref)
