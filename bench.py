@@ -359,9 +359,13 @@ def run_ours(args, rank, world, local):
         except Exception:
             traffic = None
     # CPU baseline: oracle port on the host cores, bounded sample (a few forwards of 16 images)
-    best_cpu_threads(sd)
     cpu_batch = 64
-    t_cpu = cpu_forward_timer(sd, cpu_batch, 5)
+    cpu_line = None                              # timed on rank 0 at N=1 only (the scaling runs do not repeat it)
+    if world == 1:
+        best_cpu_threads(sd)
+        t_cpu = cpu_forward_timer(sd, cpu_batch, 5)
+        cpu_line = dict(value=cpu_batch * N / t_cpu, unit="tokens/s", cores=torch.get_num_threads(), kind="port",
+                        sample=f"median of 5 forwards of {cpu_batch} images (fp32 torch CPU, ATen-op port of ViT.py:79-89)")
     out = dict(
         metric="attn-fwd tokens/sec (ViT-B N=197 d=768)", value=value, unit="tokens/s", n_gpus=world, steps=args.steps,
         warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -378,8 +382,7 @@ def run_ours(args, rank, world, local):
         phase_kernels_alone_us=kern,
         qkv_gemm_alone=dict(tflops=qkv_flops / (kern["qkv_gemm_us"] * 1e-6) / 1e12,
                             frac_of_burst_peak=qkv_flops / (kern["qkv_gemm_us"] * 1e-6) / 1e12 / peaks["bf16_tflops"]),
-        cpu_baseline=dict(value=cpu_batch * N / t_cpu, unit="tokens/s", cores=torch.get_num_threads(), kind="port",
-                          sample=f"median of 5 forwards of {cpu_batch} images (fp32 torch CPU, ATen-op port of ViT.py:79-89)"),
+        cpu_baseline=cpu_line,
         e2e=dict(value=tokens * e2e_n / e2e_dt, unit="tokens/s", h2d_bytes_per_step=B * N * C * 2, d2h_bytes_per_step=B * N * C * 2,
                  steps=e2e_n, note="pinned host x -> H2D -> forward -> D2H y each step; 3 streams, 2 slots in flight"),
         gpu_launches=int(launches),
