@@ -11,13 +11,15 @@
 // (a single block may be up to 256 wide): one block -> exact single-pass softmax; several blocks -> online
 // softmax with the running O rescaled in TMEM (cheap: HD columns per row).
 //
-// 576 threads:  warp 0 TMA producer (+ TMEM allocator) | warp 1 MMA issuer |
+// 640 threads:  warp 0 TMA producer (+ TMEM allocator) | warp 1 MMA issuer | warps 18-19 idle (register allocation granularity) |
 //               warps 2-9 softmax+epilogue of slot 0 | warps 10-17 of slot 1.  TWO threads per query row (a warp may
 //               touch TMEM lanes 32*(warp%4)..+31, so warps w and w+4 of a slot share a lane quarter): each owns one
 //               half of the row's S columns end to end -- partial max (exchanged through smem), exponentials, its half
 //               of P written IN PLACE inside its own S columns, partial row sum, its half of the O columns.
 //               Four softmax warps per scheduler instead of two: a single warp cannot keep the MUFU busy (measured).
-// TMEM slot (256 columns): S fp32 [0,kb)  ->  P fp16x2 [0,kb/2) written in place behind the S reads;
+// Softmax passes: max pass with 32-column TMEM loads; exponential pass in 16-column steps, 12 of 16 exponentials on the MUFU
+//               and 4 on the FMA pipe (degree-3 polynomial), never overlapping a TMEM load with the step's compute (measured).
+// TMEM slot (256 columns): S fp32 [0,kb)  ->  P fp16x2 written in place inside each thread's own S columns (two segments);
 //                          O fp32 [256-HD, 256) (aliases the tail of S only in the single-block case, where the
 //                          PV MMAs start after the softmax has drained S).
 #pragma once

@@ -4,7 +4,7 @@
 //     phase 3  y = O Wproj^T + b               gemm_run
 // Every persistent CTA walks its share of phase 1, then of phase 2, then of phase 3.  There is no grid-wide barrier:
 // phases are chained by dependency counters in global memory at tile granularity
-//     ctr_qkv[128-row tile of the qkv buffer]  += 1 per stored GEMM tile   -> an attention item waits for the tiles covering its image
+//     ctr_qkv[128-row tile of the qkv buffer]  += 1 per epilogue warp set of every stored GEMM tile -> an attention item waits for the tiles covering its image
 //     ctr_attn[image]                          += 1 per stored (head, query tile) -> a proj tile waits for the images covering its rows
 // so a CTA that runs out of phase-1 tiles starts attention on the first images while others finish the last GEMM tiles:
 // no partially filled last wave, no per-kernel prologue/epilogue tail, no launch gaps, intermediates stay in L2.
