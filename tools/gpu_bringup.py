@@ -195,7 +195,11 @@ def probe_attn():
 def probe_vit():
     import torch
     import pytorch_attention_b200 as pa
-    from oracle import vit_attention
+    def vit_attention(x, wq, bq, wp, bp, H):        # plain fp32 check inside the tool (oracle/ is for tests, smoke and bench only)
+        B, N, C = x.shape
+        qkv = torch.nn.functional.linear(x, wq, bq).reshape(B, N, 3, H, C // H).permute(2, 0, 3, 1, 4)
+        a = ((qkv[0] @ qkv[1].transpose(-1, -2)) * (C // H) ** -0.5).softmax(-1)
+        return torch.nn.functional.linear((a @ qkv[2]).transpose(1, 2).reshape(B, N, C), wp, bp)
     torch.manual_seed(3)
     for (B, N, C, H, dt, odt, iters) in [(2, 197, 768, 12, torch.float16, torch.float16, 20),
                                          (2, 197, 768, 12, torch.float16, torch.float32, 20),
