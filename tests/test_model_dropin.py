@@ -76,3 +76,34 @@ def test_dropin_attention_inside_the_whole_model_matches_reference_logits():
         y = vit_model_forward(sdg, x.to(dev), attn, CFG["patch_size"], CFG["depths"]).cpu()
     # the path's own tolerance is 1e-3 per attention; two blocks, fp16-rounded attention inputs and the MLP/head amplify it
     assert rel_fro(y, y_ref) < 3e-3, rel_fro(y, y_ref)
+
+
+def _swap_targets():
+    import pytorch_attention_b200 as pa
+    return {
+        "pvt": ("pvt_t", {"Attention": pa.pvt.Attention}),
+        "cvt": ("cvt_13", {"Attention": pa.cvt.Attention}),
+        "cswin": ("CSWin_64_12211_tiny_224", {"LePEAttention": pa.cswin.LePEAttention, "CSWinBlock": pa.cswin.CSWinBlock}),
+        "xcit": ("xcit_nano_12_p16", {"XCA": pa.xcit.XCA, "ClassAttention": pa.xcit.ClassAttention}),
+    }
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted")
+@pytest.mark.parametrize("modname", ["pvt", "cvt", "cswin", "xcit"])
+def test_class_swap_in_the_reference_zoo_models(modname, monkeypatch):
+    """The reference's own model constructors build the drop-ins with the reference's arguments, and a stock model's
+    state_dict loads strictly into the swapped model (same keys, same shapes) -- for every model family on the path."""
+    import importlib
+    monkeypatch.syspath_prepend(REF)
+    mod = importlib.import_module(modname)
+    factory, swaps = _swap_targets()[modname]
+    torch.manual_seed(0)
+    stock = getattr(mod, factory)()
+    sd = stock.state_dict()
+    for name, cls in swaps.items():
+        monkeypatch.setattr(mod, name, cls)
+    swapped = getattr(mod, factory)()
+    n_dropins = sum(isinstance(m, tuple(swaps.values())) for m in swapped.modules())
+    n_stock = sum(type(m).__name__ in swaps for m in stock.modules())
+    assert n_dropins == n_stock and n_dropins > 0
+    swapped.load_state_dict(sd, strict=True)
