@@ -150,7 +150,7 @@ int pa_cvt_fwd(const pa_cvt_args* a, void* workspace, size_t workspace_bytes, vo
 /* ---------------------------------------------------------------- xcit.XCA (xcit.py:233-265) and xcit.ClassAttention (xcit.py:159-188) */
 typedef struct {
   int dtype, out_dtype;
-  int B, N, C, H;            /* C / H == 64 */
+  int B, N, C, H;            /* C / H == 64 or 32 (xcit_nano_12_p16: dim 128, 4 heads) */
   float scale;               /* ClassAttention only (XCA has no head_dim scale, xcit.py:258) */
   const void* x;             /* [B,N,C] */
   const void* qkv_weight;    /* [3C,C] (dtype) */

@@ -692,7 +692,7 @@ static int xc_check(const pa_xcit_args* a, const char* who) {
   if (!a) return fail(PA_ERR_NULL, "%s: args is NULL", who);
   if (a->B <= 0 || a->N <= 0 || a->C <= 0 || a->H <= 0) return fail(PA_ERR_BAD_SHAPE, "%s: B,N,C,H must be positive", who);
   if (a->C % a->H != 0) return fail(PA_ERR_BAD_SHAPE, "%s: dim %d not divisible by num_heads %d", who, a->C, a->H);
-  if (a->C / a->H != 64) return fail(PA_ERR_UNSUPPORTED, "%s: head_dim %d unsupported (64 only)", who, a->C / a->H);
+  if (a->C / a->H != 64 && a->C / a->H != 32) return fail(PA_ERR_UNSUPPORTED, "%s: head_dim %d unsupported (64 or 32)", who, a->C / a->H);
   if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "%s: dtype must be fp16/bf16", who);
   return PA_OK;
 }
@@ -719,7 +719,8 @@ int pa_xca_fwd(const pa_xcit_args* a, void* workspace, size_t workspace_bytes, v
   if ((rc = linear(a->x, a->dtype, C, a->qkv_weight, a->dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
   XcaParams xp;
   xp.qkv = qkv; xp.out = ob; xp.temperature = a->temperature; xp.B = a->B; xp.N = a->N; xp.C = C; xp.H = a->H;
-  xca_core_kernel<<<a->B * a->H, 256, 0, st>>>(xp);
+  if (C / a->H == 64) xca_core_kernel<64><<<a->B * a->H, 256, 0, st>>>(xp);
+  else xca_core_kernel<32><<<a->B * a->H, 256, 0, st>>>(xp);
   PA_CUDA_OK(cudaGetLastError());
   launch_counter()++;
   return linear(ob, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st);
@@ -749,7 +750,8 @@ int pa_class_attn_fwd(const pa_xcit_args* a, void* workspace, size_t workspace_b
   if ((rc = linear(a->x, a->dtype, C, a->qkv_weight, a->dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
   ClsParams cp;
   cp.qkv = qkv; cp.out = cls; cp.B = a->B; cp.N = a->N; cp.C = C; cp.H = a->H; cp.scale = a->scale;
-  class_attn_core_kernel<<<a->B * a->H, 256, a->N * sizeof(float), st>>>(cp);
+  if (C / a->H == 64) class_attn_core_kernel<64><<<a->B * a->H, 256, a->N * sizeof(float), st>>>(cp);
+  else class_attn_core_kernel<32><<<a->B * a->H, 256, a->N * sizeof(float), st>>>(cp);
   PA_CUDA_OK(cudaGetLastError());
   launch_counter()++;
   // y = x (patch tokens pass through, xcit.py:187), then row 0 of every image <- proj(cls)  (xcit.py:186)

@@ -221,78 +221,81 @@ struct XcaParams {
   int B, N, C, H;
 };
 constexpr int XCA_CHUNK = 32;
+template <int HD>                       // head dim 64, or 32 (the zoo's xcit_nano: dim 128, 4 heads)
 __global__ void __launch_bounds__(256) xca_core_kernel(const XcaParams p) {
-  __shared__ float sq[XCA_CHUNK][65], sk[XCA_CHUNK][65];
-  __shared__ float A[64][65];
-  __shared__ float qn[64], kn[64];
+  constexpr int BLK = HD / 16;          // each of the 16 x 16 threads owns a BLK x BLK block of A
+  constexpr int TPR = 256 / HD;         // threads per softmax row
+  __shared__ float sq[XCA_CHUNK][HD + 1], sk[XCA_CHUNK][HD + 1];
+  __shared__ float A[HD][HD + 1];
+  __shared__ float qn[HD], kn[HD];
   const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const long long ld = 3LL * p.C;
-  const __half* base = reinterpret_cast<const __half*>(p.qkv) + (long long)b * p.N * ld + h * 64;
-  float acc[4][4] = {};
-  float nq = 0.f, nk = 0.f;         // thread tid<64: sum of squares of column tid of q; 64<=tid<128: of k
+  const __half* base = reinterpret_cast<const __half*>(p.qkv) + (long long)b * p.N * ld + h * HD;
+  float acc[BLK][BLK] = {};
+  float nq = 0.f, nk = 0.f;         // thread tid<HD: sum of squares of column tid of q; HD<=tid<2HD: of k
   for (int n0 = 0; n0 < p.N; n0 += XCA_CHUNK) {
-    for (int i = tid; i < XCA_CHUNK * 64; i += 256) {
-      const int r = i >> 6, c = i & 63;
+    for (int i = tid; i < XCA_CHUNK * HD; i += 256) {
+      const int r = i / HD, c = i % HD;
       const bool ok = (n0 + r) < p.N;
       sq[r][c] = ok ? __half2float(base[(long long)(n0 + r) * ld + c]) : 0.f;
       sk[r][c] = ok ? __half2float(base[(long long)(n0 + r) * ld + p.C + c]) : 0.f;
     }
     __syncthreads();
-    if (tid < 64) {
+    if (tid < HD) {
       for (int r = 0; r < XCA_CHUNK; ++r) nq = fmaf(sq[r][tid], sq[r][tid], nq);
-    } else if (tid < 128) {
-      for (int r = 0; r < XCA_CHUNK; ++r) nk = fmaf(sk[r][tid - 64], sk[r][tid - 64], nk);
+    } else if (tid < 2 * HD) {
+      for (int r = 0; r < XCA_CHUNK; ++r) nk = fmaf(sk[r][tid - HD], sk[r][tid - HD], nk);
     }
     for (int r = 0; r < XCA_CHUNK; ++r) {
-      float a[4], bb[4];
+      float a[BLK], bb[BLK];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = sq[r][4 * ty + i]; bb[i] = sk[r][4 * tx + i]; }
+      for (int i = 0; i < BLK; ++i) { a[i] = sq[r][BLK * ty + i]; bb[i] = sk[r][BLK * tx + i]; }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < BLK; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        for (int j = 0; j < BLK; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
     __syncthreads();
   }
-  if (tid < 64) qn[tid] = fmaxf(sqrtf(nq), 1e-12f);            // F.normalize eps (xcit.py:255)
-  else if (tid < 128) kn[tid - 64] = fmaxf(sqrtf(nk), 1e-12f);
+  if (tid < HD) qn[tid] = fmaxf(sqrtf(nq), 1e-12f);            // F.normalize eps (xcit.py:255)
+  else if (tid < 2 * HD) kn[tid - HD] = fmaxf(sqrtf(nk), 1e-12f);
   __syncthreads();
   const float temp = __ldg(p.temperature + h);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < BLK; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) A[4 * ty + i][4 * tx + j] = acc[i][j] / (qn[4 * ty + i] * kn[4 * tx + j]) * temp;
+    for (int j = 0; j < BLK; ++j) A[BLK * ty + i][BLK * tx + j] = acc[i][j] / (qn[BLK * ty + i] * kn[BLK * tx + j]) * temp;
   __syncthreads();
-  // row softmax over e: 4 threads per row, shuffle reductions
+  // row softmax over e: TPR threads per row, shuffle reductions
   {
-    const int row = tid >> 2, part = tid & 3;
+    const int row = tid / TPR, part = tid % TPR;
     float mx = -INFINITY;
-    for (int e = part; e < 64; e += 4) mx = fmaxf(mx, A[row][e]);
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    for (int e = part; e < HD; e += TPR) mx = fmaxf(mx, A[row][e]);
+#pragma unroll
+    for (int o = 1; o < TPR; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
-    for (int e = part; e < 64; e += 4) { const float ex = __expf(A[row][e] - mx); A[row][e] = ex; sum += ex; }
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    for (int e = part; e < HD; e += TPR) { const float ex = __expf(A[row][e] - mx); A[row][e] = ex; sum += ex; }
+#pragma unroll
+    for (int o = 1; o < TPR; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.f / sum;
-    for (int e = part; e < 64; e += 4) A[row][e] *= inv;
+    for (int e = part; e < HD; e += TPR) A[row][e] *= inv;
   }
   __syncthreads();
   // O[n, d] = sum_e A[d][e] v[n][e]; v streamed through sq
-  __half* outb = reinterpret_cast<__half*>(p.out) + (long long)b * p.N * p.C + h * 64;
+  __half* outb = reinterpret_cast<__half*>(p.out) + (long long)b * p.N * p.C + h * HD;
   for (int n0 = 0; n0 < p.N; n0 += XCA_CHUNK) {
-    for (int i = tid; i < XCA_CHUNK * 64; i += 256) {
-      const int r = i >> 6, c = i & 63;
+    for (int i = tid; i < XCA_CHUNK * HD; i += 256) {
+      const int r = i / HD, c = i % HD;
       sq[r][c] = (n0 + r) < p.N ? __half2float(base[(long long)(n0 + r) * ld + 2 * p.C + c]) : 0.f;
     }
     __syncthreads();
-    for (int i = tid; i < XCA_CHUNK * 64; i += 256) {
-      const int r = i >> 6, d = i & 63;
+    for (int i = tid; i < XCA_CHUNK * HD; i += 256) {
+      const int r = i / HD, d = i % HD;
       if (n0 + r < p.N) {
         float o = 0.f;
 #pragma unroll 16
-        for (int e = 0; e < 64; ++e) o = fmaf(A[d][e], sq[r][e], o);
+        for (int e = 0; e < HD; ++e) o = fmaf(A[d][e], sq[r][e], o);
         outb[(long long)(n0 + r) * p.C + d] = __float2half_rn(o);
       }
     }
@@ -306,22 +309,24 @@ struct ClsParams {
   const void* qkv; void* out;    // qkv [B, N, 3C] fp16; out [B, C] fp16
   int B, N, C, H; float scale;
 };
+template <int HD>
 __global__ void __launch_bounds__(256) class_attn_core_kernel(const ClsParams p) {
+  constexpr int NP = 256 / HD;     // token-strided partial sums per output channel
   extern __shared__ float sc[];    // [N] scores
   __shared__ float red[8];
-  __shared__ float q0[64];
+  __shared__ float q0[HD];
   const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long ld = 3LL * p.C;
-  const __half* base = reinterpret_cast<const __half*>(p.qkv) + (long long)b * p.N * ld + h * 64;
-  if (tid < 64) q0[tid] = __half2float(base[tid]);
+  const __half* base = reinterpret_cast<const __half*>(p.qkv) + (long long)b * p.N * ld + h * HD;
+  if (tid < HD) q0[tid] = __half2float(base[tid]);
   __syncthreads();
   float mx = -INFINITY;
   for (int n = tid; n < p.N; n += 256) {
     const __half* kr = base + (long long)n * ld + p.C;
     float s = 0.f;
 #pragma unroll 8
-    for (int d = 0; d < 64; ++d) s = fmaf(q0[d], __half2float(kr[d]), s);
+    for (int d = 0; d < HD; ++d) s = fmaf(q0[d], __half2float(kr[d]), s);
     s *= p.scale;
     sc[n] = s;
     mx = fmaxf(mx, s);
@@ -344,18 +349,21 @@ __global__ void __launch_bounds__(256) class_attn_core_kernel(const ClsParams p)
 #pragma unroll
   for (int w = 0; w < 8; ++w) sum += red[w];
   const float inv = 1.f / sum;
-  // cls[d] = sum_n a[n] v[n][d]: thread (part = tid/64, d = tid%64) strides over tokens, then reduce 4 parts
-  __shared__ float part[4][64];
+  // cls[d] = sum_n a[n] v[n][d]: thread (part = tid/HD, d = tid%HD) strides over tokens, then reduce the NP parts
+  __shared__ float part[NP][HD];
   {
-    const int d = tid & 63, pt = tid >> 6;
+    const int d = tid % HD, pt = tid / HD;
     float o = 0.f;
-    for (int n = pt; n < p.N; n += 4) o = fmaf(sc[n], __half2float(base[(long long)n * ld + 2 * p.C + d]), o);
+    for (int n = pt; n < p.N; n += NP) o = fmaf(sc[n], __half2float(base[(long long)n * ld + 2 * p.C + d]), o);
     part[pt][d] = o;
   }
   __syncthreads();
-  if (tid < 64)
-    reinterpret_cast<__half*>(p.out)[(long long)b * p.C + h * 64 + tid] =
-        __float2half_rn((part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid]) * inv);
+  if (tid < HD) {
+    float o = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) o += part[i][tid];
+    reinterpret_cast<__half*>(p.out)[(long long)b * p.C + h * HD + tid] = __float2half_rn(o * inv);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -76,8 +76,8 @@ def test_variant_argument_validation_without_gpu():
     le.L, le.idx = 49, 2
     assert lib.pa_cswin_lepe_fwd(C.byref(le), None) == L.PA_ERR_UNSUPPORTED         # ERROR MODE (cswin.py:68-70)
     x = L.XcitArgs()
-    x.B, x.N, x.C, x.H = 1, 8, 128, 4
-    assert lib.pa_xca_fwd(C.byref(x), None, 0, None) == L.PA_ERR_UNSUPPORTED        # head_dim 32 on the XCA path
+    x.B, x.N, x.C, x.H = 1, 8, 128, 8
+    assert lib.pa_xca_fwd(C.byref(x), None, 0, None) == L.PA_ERR_UNSUPPORTED        # head_dim 16 on the XCA path (64 and 32 exist)
     cv = L.CvtArgs()
     assert lib.pa_cvt_fwd(C.byref(cv), None, 0, None) == L.PA_ERR_BAD_SHAPE
     blk = L.CswinBlockArgs()

@@ -61,6 +61,9 @@ ORACLE_CASES = {
     # XCiT at ViT-B-like width
     "xca_768": dict(variant="xca", ctor=dict(dim=768, num_heads=12), x=(2, 196, 768)),
     "classattn_768": dict(variant="class_attn", ctor=dict(dim=768, num_heads=12), x=(2, 197, 768)),
+    # the zoo's own XCiT configuration (xcit_nano_12_p16, xcit.py:393: dim 128, 4 heads -> 32-wide heads, A is 32 x 32)
+    "xca_nano_hd32": dict(variant="xca", ctor=dict(dim=128, num_heads=4), x=(3, 196, 128)),
+    "classattn_nano_hd32": dict(variant="class_attn", ctor=dict(dim=128, num_heads=4), x=(3, 197, 128)),
 }
 
 
