@@ -50,6 +50,11 @@ const char* pa_last_error(void);
 int pa_device_check(int device);
 /* number of kernels this library has launched in the calling process (all threads). */
 unsigned long long pa_launch_count(void);
+/* The PA_* environment switches (experiments and fallbacks) are read once, at the first call into the
+ * library; this re-reads them (tests and tools that flip a switch inside one process call it). */
+void pa_reload_env(void);
+/* debug aid: occupancy facts of the co-scheduled ViT kernel (registers, static smem, blocks per SM, resident clusters, ...) */
+int pa_debug_cosched_occupancy(int dynamic_smem_bytes, int* out6);
 
 /* ---------------------------------------------------------------- building blocks (also exported for tests) */
 /* D[z][m,n] = sum_k A[z][m,k] B[z][n,k] (+bias): both operands K-major, i.e. nn.Linear / 1x1-conv layout. */

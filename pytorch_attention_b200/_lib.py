@@ -84,6 +84,8 @@ SYMBOLS = {
     "pa_last_error": (C.c_char_p, []),
     "pa_device_check": (_i, [_i]),
     "pa_launch_count": (C.c_ulonglong, []),
+    "pa_reload_env": (None, []),
+    "pa_debug_cosched_occupancy": (_i, [_i, C.POINTER(_i)]),
     "pa_gemm_tn": (_i, [C.POINTER(GemmArgs), _vp]),
     "pa_debug_set_gemm_trace": (None, [_vp]),
     "pa_attn_core": (_i, [C.POINTER(AttnArgs), _vp]),
@@ -155,3 +157,8 @@ def check(rc):
 
 def launch_count():
     return int(load().pa_launch_count())
+
+
+def reload_env():
+    """The library caches the PA_* environment switches at its first call; re-read them after changing os.environ."""
+    load().pa_reload_env()

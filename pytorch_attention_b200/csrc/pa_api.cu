@@ -2,6 +2,7 @@
 #include "pa_attn.cuh"
 #include "pa_gemm.cuh"
 #include "pa_fused.cuh"
+#include "pa_cosched.cuh"
 #include "pa_host.cuh"
 #include "pa_misc.cuh"
 
@@ -26,23 +27,80 @@ struct Arena {
   }
 };
 
+
+// ------------------------------------------------------------------------------------------------ environment switches
+// Read ONCE (first call, or pa_reload_env()): no getenv on the per-forward path.  All of them are experiments / fallbacks;
+// none changes results.
+struct EnvCfg {
+  int gemm_maxworkers = 0, gemm_cluster = 0, gemm_bn = 0, gemm_balanced = 0, gemm_debug = 0, gemm_direct_store = 0;
+  int attn_debug = 0, attn_direct_store = 0;
+  int vit_fused = -1;        // -1 unset, 0 three launches, 1 single launch required
+  int vit_cosched = -1;      // -1 unset (co-scheduled kernel when it qualifies), 0 never, 1 required
+  int fused_bn1 = 0, fused_bn2 = 0;
+  int cs_debug = 0;
+};
+std::atomic<const EnvCfg*> g_env{nullptr};
+std::mutex g_env_mu;
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+const EnvCfg* env_load() {
+  EnvCfg* c = new EnvCfg;       // a reload leaks the previous (tiny) block on purpose: concurrent readers may still hold it
+  c->gemm_maxworkers = env_int("PA_GEMM_MAXWORKERS", 0);
+  c->gemm_cluster = env_int("PA_GEMM_CLUSTER", 0);
+  c->gemm_bn = env_int("PA_GEMM_BN", 0);
+  c->gemm_balanced = getenv("PA_GEMM_BALANCED") != nullptr;
+  c->gemm_debug = env_int("PA_GEMM_DEBUG", 0);
+  c->gemm_direct_store = getenv("PA_GEMM_DIRECT_STORE") != nullptr;
+  c->attn_debug = env_int("PA_ATTN_DEBUG", 0);
+  c->attn_direct_store = getenv("PA_ATTN_DIRECT_STORE") != nullptr;
+  c->vit_fused = env_int("PA_VIT_FUSED", -1);
+  c->vit_cosched = env_int("PA_VIT_COSCHED", -1);
+  c->fused_bn1 = env_int("PA_FUSED_BN1", 0);
+  c->fused_bn2 = env_int("PA_FUSED_BN2", 0);
+  c->cs_debug = env_int("PA_CS_DEBUG", 0);
+  return c;
+}
+inline const EnvCfg& env() {
+  const EnvCfg* c = g_env.load(std::memory_order_acquire);
+  if (c) return *c;
+  std::lock_guard<std::mutex> lk(g_env_mu);
+  c = g_env.load(std::memory_order_acquire);
+  if (!c) { c = env_load(); g_env.store(c, std::memory_order_release); }
+  return *c;
+}
+
+// per-device "attribute already set" bookkeeping shared by the launchers (several host threads may drive several GPUs)
+struct SmemAttr {
+  std::mutex mu;
+  int set[64] = {0};
+  template <typename K>
+  int ensure(K kernel, int bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    std::lock_guard<std::mutex> lk(mu);
+    if (set[dev] < bytes) {
+      PA_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      set[dev] = bytes;
+    }
+    return PA_OK;
+  }
+};
+
 // ------------------------------------------------------------------------------------------------ GEMM
 template <int BN, int ST, int CL, bool PAIR = false>
 int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, GemmParams p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, ST, PAIR>;
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_done[dev & 63]) {
-    PA_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<BN, ST, CL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done[dev & 63] = true;
-  }
+  static SmemAttr smem_attr;
+  { const int rc = smem_attr.ensure(gemm_tn_kernel<BN, ST, CL, PAIR>, Cfg::SMEM_BYTES); if (rc) return rc; }
   p.m_groups = (p.m_tiles + CL - 1) / CL;
   if (!(PAIR && BN == 256)) p.balanced = 0;
   const int supertiles = p.m_groups * p.n_tiles * p.Z;
   int max_clusters = num_sms() / CL;
-  if (const char* env = getenv("PA_GEMM_MAXWORKERS")) {   // experiment: contention vs number of active workers
-    const int v = atoi(env);
+  if (const int v = env().gemm_maxworkers) {   // experiment: contention vs number of active workers
     if (v > 0 && v < max_clusters) max_clusters = v;
   }
   const int nclusters = supertiles < max_clusters ? supertiles : max_clusters;
@@ -75,18 +133,14 @@ int launch_gemm_cl(int cl, const CUtensorMap& tmA, const CUtensorMap& tmB, const
 long long* g_gemm_trace = nullptr;   // debug hook, see pa_debug_set_gemm_trace
 
 int pick_cluster(int m_tiles) {
-  const char* env = getenv("PA_GEMM_CLUSTER");
-  if (env) {
-    int v = atoi(env);
-    if (v == 1 || v == 2 || v == 4 || v == -2) return v;
-  }
+  const int v = env().gemm_cluster;
+  if (v == 1 || v == 2 || v == 4 || v == -2) return v;
   return m_tiles >= 2 ? -2 : 1;
 }
 
 int pick_block_n(int M, int N, int K, int Z, bool pair) {
-  const char* env = getenv("PA_GEMM_BN");
-  if (env) {
-    int v = atoi(env);
+  {
+    const int v = env().gemm_bn;
     if (v == 64 || v == 96 || v == 128 || v == 192 || v == 256) return v;
   }
   const int cands[5] = {256, 192, 128, 96, 64};
@@ -132,13 +186,13 @@ int gemm_prepare(const pa_gemm_args* a, GemmPlan* plan, int force_bn = 0, int fo
 
   int cl = force_cl ? force_cl : a->cluster ? a->cluster : pick_cluster((a->M + 127) / 128);
   int bn = force_bn ? force_bn : a->block_n ? a->block_n : pick_block_n(a->M, a->N, a->K, a->Z, cl == -2);
-  if (!a->block_n && cl == -2 && getenv("PA_GEMM_BALANCED")) bn = 256;   // experimental: balanced unit walk needs 256-wide tiles
+  if (!a->block_n && cl == -2 && env().gemm_balanced) bn = 256;   // experimental: balanced unit walk needs 256-wide tiles
   if (cl != 1 && cl != 2 && cl != 4 && cl != -2) return fail(PA_ERR_UNSUPPORTED, "pa_gemm_tn: cluster %d not in {1,2,4,-2}", cl);
   if (bn == 96 && cl == 4) cl = 2;          // B slices must stay whole 8-row swizzle atoms
   const bool pair = (cl == -2);             // cta_group::2: CTA pairs, 256-row tiles, each CTA stages half of B
   // balanced unit partition (32-row B boxes): measured 2 % better than the classic order at BLOCK_N 256 but worse than
   // classic BLOCK_N 192 on the ViT shapes (four small TMA boxes per k-block, less A-tile sharing in L2) -> opt-in only
-  const bool balanced = pair && bn == 256 && getenv("PA_GEMM_BALANCED");
+  const bool balanced = pair && bn == 256 && env().gemm_balanced;
   const int b_box_rows = balanced ? 32 : pair ? bn / 2 : bn / cl;
   {
     const int za = a->a_batch ? a->Z : 1;
@@ -169,11 +223,11 @@ int gemm_prepare(const pa_gemm_args* a, GemmPlan* plan, int force_bn = 0, int fo
   p.balanced = balanced ? 1 : 0;
   p.wait_ctr = nullptr; p.wait_rows = 1; p.wait_target = 0; p.signal_ctr = nullptr; p.worker_shift = 0;
   p.n_units = (a->N + 63) / 64;
-  { const char* dbg = getenv("PA_GEMM_DEBUG"); p.debug_flags = dbg ? atoi(dbg) : 0; }
+  p.debug_flags = env().gemm_debug;
   // output map for the staged TMA-store epilogue (128 x 32 sub-tiles); needs 16-byte aligned base and pitches
   const int elt = a->out_dtype == PA_DTYPE_F32 ? 4 : 2;
   p.tma_store = ((reinterpret_cast<uintptr_t>(a->D) & 15) == 0) && ((a->ldd * elt) % 16 == 0) &&
-                (a->Z == 1 || (a->d_batch * elt) % 16 == 0) && !getenv("PA_GEMM_DIRECT_STORE");
+                (a->Z == 1 || (a->d_batch * elt) % 16 == 0) && !env().gemm_direct_store;
   tmD = tmA;
   if (p.tma_store) {
     uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->Z};
@@ -234,13 +288,8 @@ struct AttnLaunch {
 template <int HD, bool WIN>
 int launch_attn_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
                   const AttnParams& p, int smem, cudaStream_t st) {
-  static int attr_smem[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (attr_smem[dev & 63] < smem) {
-    PA_CUDA_OK(cudaFuncSetAttribute(attn_core_kernel<HD, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem[dev & 63] = smem;
-  }
+  static SmemAttr smem_attr;
+  { const int rc = smem_attr.ensure(attn_core_kernel<HD, WIN>, smem); if (rc) return rc; }
   const int grid = p.items < num_sms() ? p.items : num_sms();
   attn_core_kernel<HD, WIN><<<grid, ATTN_THREADS, smem, st>>>(tq, tk, tv, to, p);
   PA_CUDA_OK(cudaGetLastError());
@@ -275,7 +324,7 @@ int attn_prepare(const AttnLaunch& a, AttnPlan* plan) {
   p.scale_log2e = a.scale * 1.4426950408889634f;
   p.add_into_out = a.add_into_out;
   p.trace = g_gemm_trace;
-  { const char* dbg = getenv("PA_ATTN_DEBUG"); p.debug_flags = dbg ? atoi(dbg) : 0; }
+  p.debug_flags = env().attn_debug;
   if (!a.windowed) {
     p.G = a.G; p.n_q = a.n_q; p.n_k = a.n_k;
     if (a.n_k <= 256) { p.nkb = 1; p.kb = (a.n_k + 15) / 16 * 16; }
@@ -328,7 +377,7 @@ int attn_prepare(const AttnLaunch& a, AttnPlan* plan) {
   p.idesc_s = make_idesc(128, p.kb, PA_F16, PA_F16, 0, 0);
   p.idesc_o = make_idesc(128, hd, PA_F16, PA_F16, 0, 1);
   // staged TMA-store epilogue when the plan still fits (and rows are consecutive tokens), else direct stores
-  bool staged = !a.windowed && !getenv("PA_ATTN_DIRECT_STORE") &&
+  bool staged = !a.windowed && !env().attn_direct_store &&
                 attn_smem_bytes(hd, false, p.nkb, p.kb, p.kb_rows, true) <= 227 * 1024;
   const int smem = attn_smem_bytes(hd, a.windowed, p.nkb, p.kb, p.kb_rows, staged);
   if (smem > 227 * 1024) return fail(PA_ERR_UNSUPPORTED, "attention core: shared memory plan %d B too large", smem);
@@ -401,13 +450,8 @@ static int fused_pick_bn(int M, int N, int K) {
 
 template <int BN1, int BN2>
 static int launch_vit_fused(const GemmPlan& p1, const AttnPlan& pa_, const GemmPlan& p2, const VitFusedParams& fp, int smem, cudaStream_t st) {
-  static int attr_done[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (attr_done[dev & 63] < smem) {
-    PA_CUDA_OK(cudaFuncSetAttribute(vit_fused_kernel<BN1, BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done[dev & 63] = smem;
-  }
+  static SmemAttr smem_attr;
+  { const int rc = smem_attr.ensure(vit_fused_kernel<BN1, BN2>, smem); if (rc) return rc; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((num_sms() / 2) * 2);
   cfg.blockDim = dim3(ATTN_THREADS);
@@ -422,6 +466,66 @@ static int launch_vit_fused(const GemmPlan& p1, const AttnPlan& pa_, const GemmP
   return PA_OK;
 }
 
+
+// Co-scheduled single launch (pa_cosched.cuh): 2 CTAs per SM in clusters of 2.  Returns 1 when the configuration cannot be
+// guaranteed fully co-resident on this device (the caller then uses the sequenced kernel), 0 on success, < 0 on error.
+// cudaOccupancyMaxActiveClusters cannot answer the question: for any kernel that executes tcgen05.alloc it reports one CTA per
+// SM (measured on B200 / CUDA 12.9: tools/occ_probe.cu), although two CTAs that allocate 256 TMEM columns each are placed
+// on every SM.  So residency is established once per device and shared-memory size by the kernel itself in probe mode
+// (no work: every CTA allocates its TMEM, announces itself and waits up to ~5 ms to see the whole grid) -- one launch and
+// one stream synchronisation at the first qualifying call; never inside a stream capture (that call takes the other path).
+static int launch_vit_cosched(const GemmPlan& p1, const CUtensorMap& tmD1, const AttnPlan& pa_, const GemmPlan& p2, const CUtensorMap& tmD2,
+                              CsParams cp, int smem, cudaStream_t st) {
+  struct DevState { int smem_set = 0; int probed_smem = 0; int resident = 0; };
+  static DevState state[64];
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  const int grid = (num_sms() / 2) * 4;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(CS_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    DevState& ds = state[dev];
+    if (ds.smem_set < smem) {
+      PA_CUDA_OK(cudaFuncSetAttribute(vit_cosched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      PA_CUDA_OK(cudaFuncSetAttribute(vit_cosched_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      ds.smem_set = smem;
+    }
+    if (ds.probed_smem < smem) {
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      PA_CUDA_OK(cudaStreamIsCapturing(st, &cap));
+      if (cap != cudaStreamCaptureStatusNone) return 1;           // cannot synchronise here: not established yet
+      // the scheduling words were zeroed by the caller's memset on this stream; the probe counters live behind them
+      CsParams pp = cp;
+      pp.probe = cp.sched + cs_sched_ints(grid);
+      PA_CUDA_OK(cudaMemsetAsync(pp.probe, 0, 2 * sizeof(int), st));
+      PA_CUDA_OK(cudaLaunchKernelEx(&cfg, vit_cosched_kernel, p1.tmA, p1.tmB, tmD1, pa_.tq, pa_.tk, pa_.tv, pa_.to, p2.tmA, p2.tmB, tmD2, pp));
+      int seen[2] = {0, 0};
+      PA_CUDA_OK(cudaMemcpyAsync(seen, pp.probe, sizeof(seen), cudaMemcpyDeviceToHost, st));
+      PA_CUDA_OK(cudaStreamSynchronize(st));
+      ds.probed_smem = smem;
+      ds.resident = (seen[1] == grid);
+      // the probe launch consumed the role tickets: zero them again for the real launch
+      PA_CUDA_OK(cudaMemsetAsync(cp.sched, 0, (size_t)cs_sched_ints(grid) * sizeof(int), st));
+    }
+    if (!ds.resident) {
+      fail(PA_ERR_UNSUPPORTED, "co-scheduled kernel: the residency probe did not see %d CTAs (2 per SM) resident at once (dynamic smem %d B)", grid, smem);
+      return 1;
+    }
+  }
+  cp.probe = nullptr;
+  PA_CUDA_OK(cudaLaunchKernelEx(&cfg, vit_cosched_kernel, p1.tmA, p1.tmB, tmD1, pa_.tq, pa_.tk, pa_.tv, pa_.to, p2.tmA, p2.tmB, tmD2, cp));
+  return PA_OK;
+}
 
 extern "C" {
 
@@ -455,10 +559,16 @@ static int vit_check(const pa_vit_args* a) {
   return PA_OK;
 }
 
+// dependency counters (per 128-row tile of qkv + per image) followed by the co-scheduled kernel's scheduling words
+static size_t vit_counter_ints(const pa_vit_args* a) {
+  const size_t rows = (size_t)a->B * a->N;
+  return (rows + 127) / 128 + a->B + cs_sched_ints(4 * 1024) + 2;
+}
+
 size_t pa_vit_workspace_bytes(const pa_vit_args* a) {
   if (vit_check(a)) return 0;
   const size_t rows = (size_t)a->B * a->N;
-  return align_up(rows * 3 * a->C * 2, 1024) + align_up(rows * a->C * 2, 1024) + align_up(((rows + 127) / 128 + a->B) * 4, 1024) + 1024;
+  return align_up(rows * 3 * a->C * 2, 1024) + align_up(rows * a->C * 2, 1024) + align_up(vit_counter_ints(a) * 4, 1024) + 1024;
 }
 
 int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, void* stream) {
@@ -473,28 +583,29 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
   Arena ws(workspace);
   void* qkv = ws.take((size_t)rows * 3 * C * 2);
   void* obuf = ws.take((size_t)rows * C * 2);
-  int* counters = reinterpret_cast<int*>(ws.take(((size_t)(rows + 127) / 128 + a->B) * sizeof(int)));
-  // ---- the whole forward as ONE launch (pa_fused.cuh), phases chained by dependency counters.  Default whenever the shape
-  //      qualifies (single key block, staged epilogues); PA_VIT_FUSED=0 selects the three-launch path, =1 makes a
-  //      non-qualifying shape an error instead of a silent switch to the three launches.
-  const char* fused_env = getenv("PA_VIT_FUSED");
-  const bool fused_forced = fused_env && atoi(fused_env) != 0;
-  const bool fused_wanted = fused_env ? fused_forced : true;
+  int* counters = reinterpret_cast<int*>(ws.take(vit_counter_ints(a) * sizeof(int)));
+  const int n_mt = (int)((rows + 127) / 128);
+  const EnvCfg& ev = env();
+  // ---- single-launch paths.  Default whenever the shape qualifies: the co-scheduled kernel (pa_cosched.cuh: projection
+  //      GEMMs under the softmax chain, two role-specialised CTAs per SM), else the sequenced kernel (pa_fused.cuh: the three
+  //      phases back to back per SM).  PA_VIT_FUSED=0 selects three launches, =1 makes a shape no single-launch kernel
+  //      takes an error instead of a silent switch; PA_VIT_COSCHED=0 / 1 never / always takes the co-scheduled kernel.
+  const bool fused_forced = ev.vit_fused > 0 || ev.vit_cosched > 0;
+  const bool fused_wanted = ev.vit_fused != 0;
   bool fused_ok = fused_wanted && a->N <= 256;
-  if (fused_forced && !fused_ok) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(fused): N=%d > 256 needs several key blocks", a->N);
+  if (fused_forced && !fused_ok) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(single launch): N=%d > 256 needs several key blocks", a->N);
   if (fused_ok) {
     if ((rc = current_device_check())) return rc;
-    const int n_mt = (int)((rows + 127) / 128);
     pa_gemm_args g1 = {};
     g1.a_dtype = a->dtype; g1.b_dtype = a->dtype; g1.out_dtype = PA_DTYPE_F16;
     g1.M = (int)rows; g1.N = 3 * C; g1.K = C; g1.Z = 1;
     g1.A = a->x; g1.lda = C; g1.B = a->qkv_weight; g1.ldb = C; g1.D = qkv; g1.ldd = 3 * C;
     g1.bias = a->qkv_bias; g1.bias_mode = a->qkv_bias ? 1 : 0;
-    GemmPlan p1;
-    int bn1 = fused_pick_bn((int)rows, 3 * C, C), bn2 = fused_pick_bn((int)rows, C, C);
-    if (const char* e = getenv("PA_FUSED_BN1")) { const int v = atoi(e); if (v == 192 || v == 256) bn1 = v; }   // experiments
-    if (const char* e = getenv("PA_FUSED_BN2")) { const int v = atoi(e); if (v == 192 || v == 256) bn2 = v; }
-    if ((rc = gemm_prepare(&g1, &p1, bn1, -2))) return rc;
+    pa_gemm_args g2 = {};
+    g2.a_dtype = PA_DTYPE_F16; g2.b_dtype = PA_DTYPE_F16; g2.out_dtype = a->out_dtype;
+    g2.M = (int)rows; g2.N = C; g2.K = C; g2.Z = 1;
+    g2.A = obuf; g2.lda = C; g2.B = a->proj_weight; g2.ldb = C; g2.D = a->y; g2.ldd = C;
+    g2.bias = a->proj_bias; g2.bias_mode = a->proj_bias ? 1 : 0;
     AttnLaunch al = {};
     al.hd = 64; al.G = a->B; al.H = a->H; al.n_q = a->N; al.n_k = a->N;
     al.q = qkv; al.ldq = 3 * C; al.q_group = (long long)a->N * 3 * C; al.q_col0 = 0;
@@ -503,16 +614,71 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
     al.scale = a->scale;
     AttnPlan pa_;
     if ((rc = attn_prepare(al, &pa_))) return rc;
+    const int grid_cs = (num_sms() / 2) * 4;
+    // ---------------- co-scheduled kernel
+    bool cs_ok = ev.vit_cosched != 0 && pa_.p.tma_store && pa_.p.kb <= 240 && C % 64 == 0 && a->out_dtype != PA_DTYPE_F32 &&
+                 cs_smem_bytes(pa_.p.kb) <= 112 * 1024 && grid_cs <= 4 * 1024;
+    if (ev.vit_cosched > 0 && !cs_ok)
+      return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(co-scheduled): needs N <= 240, dim %% 64 == 0, a 16-bit y and 16-byte aligned buffers");
+    if (cs_ok) {
+      GemmPlan p1, p2;
+      if ((rc = gemm_prepare(&g1, &p1, 256, -2))) return rc;
+      if ((rc = gemm_prepare(&g2, &p2, 256, -2))) return rc;
+      CUtensorMap tmD1, tmD2;                 // per-warp output boxes: 32 columns x 32 rows, 64-byte swizzle
+      {
+        uint64_t dims[3] = {(uint64_t)(3 * C), (uint64_t)rows, 1};
+        uint64_t str[2] = {(uint64_t)(3 * C) * 2, (uint64_t)(3 * C) * 2 * (uint64_t)rows};
+        uint32_t box[3] = {32, 32, 1};
+        if ((rc = make_tmap_16b(&tmD1, PA_DTYPE_F16, qkv, 3, dims, str, box, TM_SWZ_64))) return rc;
+      }
+      if (p2.p.tma_store) {
+        uint64_t dims[3] = {(uint64_t)C, (uint64_t)rows, 1};
+        uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)C * 2 * (uint64_t)rows};
+        uint32_t box[3] = {32, 32, 1};
+        if ((rc = make_tmap_16b(&tmD2, a->out_dtype, a->y, 3, dims, str, box, TM_SWZ_64))) return rc;
+      } else {
+        cs_ok = false;
+      }
+      if (cs_ok) {
+        CsParams cp = {};
+        const GemmPlan* gp[2] = {&p1, &p2};
+        for (int i = 0; i < 2; ++i) {
+          CsGemmPhase& g = cp.g[i];
+          g.M = gp[i]->p.M; g.N = gp[i]->p.N;
+          g.m_tiles = gp[i]->p.m_tiles; g.m_groups = (g.m_tiles + 1) / 2; g.n_tiles = (g.N + CS_BN - 1) / CS_BN;
+          g.tiles = g.m_groups * g.n_tiles;
+          g.bias = gp[i]->p.bias; g.out_dtype = gp[i]->p.out_dtype; g.idesc = gp[i]->p.idesc;
+        }
+        cp.K = C;
+        cp.d[0] = qkv; cp.d[1] = a->y;
+        cp.at = pa_.p;
+        cp.g[0].signal_ctr = counters;                       // per 128-row tile of qkv: every epilogue warp of every column tile
+        cp.at.wait_ctr = counters; cp.at.wait_target = cp.g[0].n_tiles * CS_EPI_WARPS;
+        cp.at.wait_rows_per_group = a->N;
+        cp.at.signal_ctr = counters + n_mt;                  // per image: one count per (head, query tile)
+        cp.g[1].wait_ctr = counters + n_mt; cp.g[1].wait_rows = a->N; cp.g[1].wait_target = a->H * cp.at.q_tiles;
+        cp.sched = counters + n_mt + a->B;
+        cp.trace = g_gemm_trace;
+        cp.debug = ev.cs_debug;
+        if (cp.debug & 1) cp.g[1].wait_ctr = nullptr;       // experiments: the idle role's dependants must not wait for it
+        if (cp.debug & 2) cp.at.wait_ctr = nullptr;
+        PA_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)(n_mt + a->B + cs_sched_ints(grid_cs)) * sizeof(int), st));
+        rc = launch_vit_cosched(p1, tmD1, pa_, p2, tmD2, cp, cs_smem_bytes(pa_.p.kb) + 1024, st);
+        if (rc < 0) return rc;
+        if (rc == 0) { launch_counter()++; return PA_OK; }
+        if (ev.vit_cosched > 0) return PA_ERR_UNSUPPORTED;    // message set by launch_vit_cosched
+      }
+    }
+    // ---------------- sequenced kernel
     if (!pa_.p.tma_store) {
       if (fused_forced) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(fused): staged attention epilogue does not fit");
       fused_ok = false;
     }
-    pa_gemm_args g2 = {};
-    g2.a_dtype = PA_DTYPE_F16; g2.b_dtype = PA_DTYPE_F16; g2.out_dtype = a->out_dtype;
-    g2.M = (int)rows; g2.N = C; g2.K = C; g2.Z = 1;
-    g2.A = obuf; g2.lda = C; g2.B = a->proj_weight; g2.ldb = C; g2.D = a->y; g2.ldd = C;
-    g2.bias = a->proj_bias; g2.bias_mode = a->proj_bias ? 1 : 0;
-    GemmPlan p2;
+    GemmPlan p1, p2;
+    int bn1 = fused_pick_bn((int)rows, 3 * C, C), bn2 = fused_pick_bn((int)rows, C, C);
+    if (ev.fused_bn1 == 192 || ev.fused_bn1 == 256) bn1 = ev.fused_bn1;     // experiments
+    if (ev.fused_bn2 == 192 || ev.fused_bn2 == 256) bn2 = ev.fused_bn2;
+    if ((rc = gemm_prepare(&g1, &p1, bn1, -2))) return rc;
     if ((rc = gemm_prepare(&g2, &p2, bn2, -2))) return rc;
     const int smem = bn1 == 256 ? (bn2 == 256 ? vit_fused_smem_bytes<256, 256>(pa_.p.kb) : vit_fused_smem_bytes<256, 192>(pa_.p.kb))
                                 : (bn2 == 256 ? vit_fused_smem_bytes<192, 256>(pa_.p.kb) : vit_fused_smem_bytes<192, 192>(pa_.p.kb));
@@ -521,34 +687,34 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
       fused_ok = false;
     }
     if (fused_ok) {
-    PA_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)(n_mt + a->B) * sizeof(int), st));
-    VitFusedParams fp;
-    fp.g1 = p1.p; fp.at = pa_.p; fp.g2 = p2.p;
-    fp.g1.m_groups = (fp.g1.m_tiles + 1) / 2; fp.g1.balanced = 0;
-    fp.g2.m_groups = (fp.g2.m_tiles + 1) / 2; fp.g2.balanced = 0;
-    if (g_gemm_trace) { fp.g1.trace = g_gemm_trace; fp.at.trace = g_gemm_trace + 512; fp.g2.trace = g_gemm_trace + 1024; }
-    {
-      // static balance: each phase's remainder units (the CTAs that get one unit more than the others) are placed on
-      // different CTAs -- qkv extras on pairs [0, r1), attention extras on the CTAs after them, and the proj phase
-      // rotated so that its light pairs are the ones that were heavy before
-      const int grid = (num_sms() / 2) * 2, ncl = grid / 2;
-      const int r1 = (fp.g1.m_groups * fp.g1.n_tiles) % ncl;
-      const int r3 = (fp.g2.m_groups * fp.g2.n_tiles) % ncl;
-      fp.at.cta_shift = (2 * r1) % grid;
-      fp.g2.worker_shift = r3;
-    }
-    fp.g1.signal_ctr = counters;                                   // per 128-row tile of qkv
-    fp.at.wait_ctr = counters; fp.at.wait_target = fp.g1.n_tiles * FUSED_ESETS;   // every epilogue set of every column tile publishes
-    fp.at.wait_rows_per_group = a->N;
-    fp.at.signal_ctr = counters + n_mt;                            // per image
-    fp.g2.wait_ctr = counters + n_mt; fp.g2.wait_rows = a->N; fp.g2.wait_target = a->H * fp.at.q_tiles;
-    if (bn1 == 256 && bn2 == 192) rc = launch_vit_fused<256, 192>(p1, pa_, p2, fp, smem, st);
-    else if (bn1 == 256) rc = launch_vit_fused<256, 256>(p1, pa_, p2, fp, smem, st);
-    else if (bn2 == 256) rc = launch_vit_fused<192, 256>(p1, pa_, p2, fp, smem, st);
-    else rc = launch_vit_fused<192, 192>(p1, pa_, p2, fp, smem, st);
-    if (rc) return rc;
-    launch_counter()++;
-    return PA_OK;
+      PA_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)(n_mt + a->B) * sizeof(int), st));
+      VitFusedParams fp;
+      fp.g1 = p1.p; fp.at = pa_.p; fp.g2 = p2.p;
+      fp.g1.m_groups = (fp.g1.m_tiles + 1) / 2; fp.g1.balanced = 0;
+      fp.g2.m_groups = (fp.g2.m_tiles + 1) / 2; fp.g2.balanced = 0;
+      if (g_gemm_trace) { fp.g1.trace = g_gemm_trace; fp.at.trace = g_gemm_trace + 512; fp.g2.trace = g_gemm_trace + 1024; }
+      {
+        // static balance: each phase's remainder units (the CTAs that get one unit more than the others) are placed on
+        // different CTAs -- qkv extras on pairs [0, r1), attention extras on the CTAs after them, and the proj phase
+        // rotated so that its light pairs are the ones that were heavy before
+        const int grid = (num_sms() / 2) * 2, ncl = grid / 2;
+        const int r1 = (fp.g1.m_groups * fp.g1.n_tiles) % ncl;
+        const int r3 = (fp.g2.m_groups * fp.g2.n_tiles) % ncl;
+        fp.at.cta_shift = (2 * r1) % grid;
+        fp.g2.worker_shift = r3;
+      }
+      fp.g1.signal_ctr = counters;                                   // per 128-row tile of qkv
+      fp.at.wait_ctr = counters; fp.at.wait_target = fp.g1.n_tiles * FUSED_ESETS;   // every epilogue set of every column tile publishes
+      fp.at.wait_rows_per_group = a->N;
+      fp.at.signal_ctr = counters + n_mt;                            // per image
+      fp.g2.wait_ctr = counters + n_mt; fp.g2.wait_rows = a->N; fp.g2.wait_target = a->H * fp.at.q_tiles;
+      if (bn1 == 256 && bn2 == 192) rc = launch_vit_fused<256, 192>(p1, pa_, p2, fp, smem, st);
+      else if (bn1 == 256) rc = launch_vit_fused<256, 256>(p1, pa_, p2, fp, smem, st);
+      else if (bn2 == 256) rc = launch_vit_fused<192, 256>(p1, pa_, p2, fp, smem, st);
+      else rc = launch_vit_fused<192, 192>(p1, pa_, p2, fp, smem, st);
+      if (rc) return rc;
+      launch_counter()++;
+      return PA_OK;
     }
   }
   // ---- three launches (any N; also the reference point the fused kernel is tested against)
@@ -564,6 +730,33 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
   if ((rc = attn_launch(at, st))) return rc;
   // 3. y = O Wproj^T + b                       (ViT.py:87)
   return linear(obuf, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st);
+}
+
+/* debug: occupancy facts of the co-scheduled kernel for `smem` bytes of dynamic shared memory; out[0..5] = registers per thread,
+ * static shared bytes, resident blocks per SM (plain launch), resident clusters of 2 (device-wide), max threads per block,
+ * binary version */
+int pa_debug_cosched_occupancy(int smem, int* out) {
+  cudaFuncAttributes fa;
+  PA_CUDA_OK(cudaFuncGetAttributes(&fa, vit_cosched_kernel));
+  PA_CUDA_OK(cudaFuncSetAttribute(vit_cosched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  PA_CUDA_OK(cudaFuncSetAttribute(vit_cosched_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int nb = -1, nc = -1;
+  PA_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, vit_cosched_kernel, CS_THREADS, smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((num_sms() / 2) * 4); cfg.blockDim = dim3(CS_THREADS); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  PA_CUDA_OK(cudaOccupancyMaxActiveClusters(&nc, vit_cosched_kernel, &cfg));
+  out[0] = fa.numRegs; out[1] = (int)fa.sharedSizeBytes; out[2] = nb; out[3] = nc; out[4] = fa.maxThreadsPerBlock; out[5] = fa.binaryVersion;
+  return PA_OK;
+}
+
+/* re-read the PA_* environment switches (they are cached at the first call) */
+void pa_reload_env(void) {
+  std::lock_guard<std::mutex> lk(g_env_mu);
+  g_env.store(env_load(), std::memory_order_release);
 }
 
 // ================================================================ PVT  (pvt.py:52-91)
