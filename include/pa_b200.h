@@ -103,14 +103,21 @@ typedef struct {
   const float* proj_bias;    /* [C] fp32 or NULL */
   void* y;                   /* [B,N,C] */
 } pa_vit_args;
-/* One kernel launch when N <= 256 (qkv GEMM -> attention -> proj GEMM phases of a persistent kernel, ordered across SMs by
- * dependency counters kept in the workspace, which the call zeroes with a cudaMemsetAsync on the same stream); three
- * stream-ordered launches otherwise.  Both give bit-identical results.  Environment: PA_VIT_FUSED=0 forces the three
- * launches, PA_VIT_FUSED=1 turns a shape the fused kernel cannot take into PA_ERR_UNSUPPORTED instead of switching.
- * The fused kernel occupies every SM with one resident CTA and spin-waits between its phases: do not make another
- * kernel that runs concurrently on the same device wait for this call (it would only be delayed, never deadlocked,
- * by kernels that finish on their own). */
+/* One kernel launch when N <= 256, three stream-ordered launches otherwise; all paths give bit-identical results.
+ *   co-scheduled kernel (default when N <= 240, C % 64 == 0, 16-bit y): two role-specialised CTAs per SM -- the qkv / proj
+ *     GEMM stream (CTA pairs, 256 TMEM columns) runs under the softmax chain of the attention stream (256 TMEM columns);
+ *   sequenced kernel (otherwise): qkv GEMM -> attention -> proj GEMM phases back to back on every SM.
+ * Both order their work across SMs by dependency counters kept in the workspace (zeroed by a cudaMemsetAsync on the same
+ * stream) and spin-wait on them, so they need every CTA of their grid resident at once: the library launches them only on
+ * a grid it has established to fit (the co-scheduled kernel: a one-off probe launch + stream synchronisation at the first
+ * qualifying call per device, skipped -- together with that kernel -- while the stream is being captured).  A kernel
+ * that holds SMs at the same time delays them; a wait that makes no progress for ~2 s (4e9 cycles) traps with a message
+ * instead of hanging the device, which poisons the CUDA context: do not co-run them with long-lived persistent kernels.
+ * Environment (read once, see pa_reload_env): PA_VIT_FUSED=0 three launches, =1 a single launch or PA_ERR_UNSUPPORTED;
+ * PA_VIT_COSCHED=0 never / =1 always the co-scheduled kernel (or PA_ERR_UNSUPPORTED). */
 size_t pa_vit_workspace_bytes(const pa_vit_args* a);
+/* 1 = three launches, 2 = sequenced single launch, 3 = co-scheduled single launch: what the calling thread's last pa_vit_fwd did */
+int pa_last_vit_path(void);
 int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- pvt.Attention  (pvt.py:52-91) */

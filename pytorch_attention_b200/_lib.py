@@ -90,6 +90,7 @@ SYMBOLS = {
     "pa_debug_set_gemm_trace": (None, [_vp]),
     "pa_attn_core": (_i, [C.POINTER(AttnArgs), _vp]),
     "pa_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitArgs)]),
+    "pa_last_vit_path": (_i, []),
     "pa_vit_fwd": (_i, [C.POINTER(VitArgs), _vp, C.c_size_t, _vp]),
     "pa_pvt_workspace_bytes": (C.c_size_t, [C.POINTER(PvtArgs)]),
     "pa_pvt_fwd": (_i, [C.POINTER(PvtArgs), _vp, C.c_size_t, _vp]),

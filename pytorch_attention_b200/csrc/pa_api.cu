@@ -131,6 +131,7 @@ int launch_gemm_cl(int cl, const CUtensorMap& tmA, const CUtensorMap& tmB, const
 }
 
 long long* g_gemm_trace = nullptr;   // debug hook, see pa_debug_set_gemm_trace
+thread_local int t_last_vit_path = 0; // which path the calling thread's last pa_vit_fwd took (see pa_last_vit_path)
 
 int pick_cluster(int m_tiles) {
   const int v = env().gemm_cluster;
@@ -665,7 +666,7 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
         PA_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)(n_mt + a->B + cs_sched_ints(grid_cs)) * sizeof(int), st));
         rc = launch_vit_cosched(p1, tmD1, pa_, p2, tmD2, cp, cs_smem_bytes(pa_.p.kb) + 1024, st);
         if (rc < 0) return rc;
-        if (rc == 0) { launch_counter()++; return PA_OK; }
+        if (rc == 0) { launch_counter()++; t_last_vit_path = 3; return PA_OK; }
         if (ev.vit_cosched > 0) return PA_ERR_UNSUPPORTED;    // message set by launch_vit_cosched
       }
     }
@@ -714,9 +715,11 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
       else rc = launch_vit_fused<192, 192>(p1, pa_, p2, fp, smem, st);
       if (rc) return rc;
       launch_counter()++;
+      t_last_vit_path = 2;
       return PA_OK;
     }
   }
+  t_last_vit_path = 1;
   // ---- three launches (any N; also the reference point the fused kernel is tested against)
   // 1. qkv[B*N, 3C] = x Wqkv^T (+b)          (ViT.py:81)
   if ((rc = linear(a->x, a->dtype, C, a->qkv_weight, a->dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
@@ -752,6 +755,10 @@ int pa_debug_cosched_occupancy(int smem, int* out) {
   out[0] = fa.numRegs; out[1] = (int)fa.sharedSizeBytes; out[2] = nb; out[3] = nc; out[4] = fa.maxThreadsPerBlock; out[5] = fa.binaryVersion;
   return PA_OK;
 }
+
+/* which path the calling thread's last successful pa_vit_fwd took: 1 three launches, 2 sequenced single launch, 3 co-scheduled
+ * single launch (0: none yet) */
+int pa_last_vit_path(void) { return t_last_vit_path; }
 
 /* re-read the PA_* environment switches (they are cached at the first call) */
 void pa_reload_env(void) {

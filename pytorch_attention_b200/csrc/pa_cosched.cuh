@@ -202,39 +202,47 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
       acc_phase ^= 1;
       tc_fence_after();
       if (tracer) CS_TRACE_G(tseq, 4);
-      // four 32-column chunks per warp, the TMEM load of chunk j+1 in flight while chunk j is converted, staged in the
-      // warp's private 2 KB tile (64-byte swizzle) and sent off as one bulk store.  (Storing the rows straight from
-      // registers was measured too: drain 2.9 k -> 5.5 k cycles, 32 scattered 16-byte segments per store instruction.)
-      uint32_t va[32], vb[32];
-      tmem_ld32(t_base + half * 32, va);
+      // Four 32-column chunks per warp: TMEM -> registers -> the warp's private 2 KB staging tile (64-byte swizzle) -> one bulk
+      // store.  With two CTAs of 113 KB on the SM there is no L1 left: the column biases come from L2, so the 8 x 16-byte
+      // bias loads of chunk j+1 are issued while chunk j is converted and staged (measured: biased tiles drained in 4.6 k
+      // cycles with the loads in line, unbiased ones in 3.0 k).  Measured and rejected: the TMEM load of chunk j+1 in flight
+      // during chunk j (no gain), rows stored straight from registers (drain 2.9 k -> 5.5 k cycles).
       const bool rows_ok = row0 < g.M;
+      const bool has_bias = g.bias != nullptr;
+      float4 bq[8];
+      if (has_bias && nt * CS_BN + half * 32 < g.N) {
 #pragma unroll
+        for (int i = 0; i < 8; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(g.bias + nt * CS_BN + half * 32) + i);
+      }
+#pragma unroll 1
       for (int j = 0; j < CS_BN / 64; ++j) {
         const int c = half * 32 + j * 64;
         const int col = nt * CS_BN + c;
+        uint32_t v[32];
+        tmem_ld32(t_base + c, v);
         tmem_ld_wait();
-        uint32_t(&v)[32] = (j & 1) ? vb : va;
-        if (j + 1 < CS_BN / 64) {
-          tmem_ld32(t_base + c + 64, (j & 1) ? va : vb);
-        } else {
-          // this warp's last TMEM read of the tile has completed: hand the accumulator back before converting the chunk
+        if (j == CS_BN / 64 - 1) {
+          // this warp's last TMEM read of the tile: hand the accumulator back before converting the chunk
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(tempty_bar);
           if (tracer) CS_TRACE_G(tseq, 5);
         }
         if (col < g.N && rows_ok) {
-          if (g.bias != nullptr) {
+          if (has_bias) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col) + i);
-              v[4 * i] = __float_as_uint(__uint_as_float(v[4 * i]) + b.x);
-              v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + b.y);
-              v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + b.z);
-              v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + b.w);
+              v[4 * i] = __float_as_uint(__uint_as_float(v[4 * i]) + bq[i].x);
+              v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + bq[i].y);
+              v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + bq[i].z);
+              v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + bq[i].w);
+            }
+            if (j + 1 < CS_BN / 64 && col + 64 < g.N) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(g.bias + col + 64) + i);
             }
           }
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile read by the previous store
+          if (lane == 0 && !(P.debug & 4)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile read by the previous store
           __syncwarp();
           uint8_t* rowp = wbuf + lane * 64;
 #pragma unroll
@@ -248,7 +256,7 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(P.debug & 8)) {
             asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                              reinterpret_cast<uint64_t>(tD)),
                          "r"(smem_u32(wbuf)), "r"(col), "r"(row0), "r"(0)

@@ -133,10 +133,16 @@ def test_gemm_unaligned_output_pitch():
 def test_gemm_balanced_walk_env(monkeypatch):
     """Opt-in balanced 64-column-unit tile walk (variable-width tiles, 32-row B boxes) is bit-exact too."""
     ops = _ops()
+    from pytorch_attention_b200 import _lib
     monkeypatch.setenv("PA_GEMM_BALANCED", "1")
-    torch.manual_seed(10)
-    M, N, K = 3000, 840, 320
-    A = torch.randint(-3, 4, (M, K), device="cuda").half()
-    B = torch.randint(-3, 4, (N, K), device="cuda").half()
-    D = ops.gemm_tn(A, B, out_dtype=torch.float32)
-    assert torch.equal(D, A.float() @ B.float().t())
+    _lib.reload_env()                      # the switches are cached by the library
+    try:
+        torch.manual_seed(10)
+        M, N, K = 3000, 840, 320
+        A = torch.randint(-3, 4, (M, K), device="cuda").half()
+        B = torch.randint(-3, 4, (N, K), device="cuda").half()
+        D = ops.gemm_tn(A, B, out_dtype=torch.float32)
+        assert torch.equal(D, A.float() @ B.float().t())
+    finally:
+        monkeypatch.delenv("PA_GEMM_BALANCED")
+        _lib.reload_env()

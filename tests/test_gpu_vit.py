@@ -123,30 +123,84 @@ def test_swap_into_reference_shaped_block():
     m.load_state_dict(ref_like.state_dict())
 
 
+def _setenv(monkeypatch, **kw):
+    """The library caches the PA_* switches: change the environment, then make it re-read them."""
+    from pytorch_attention_b200 import _lib
+    for k, v in kw.items():
+        if v is None:
+            monkeypatch.delenv(k, raising=False)
+        else:
+            monkeypatch.setenv(k, str(v))
+    _lib.reload_env()
+
+
 @pytest.mark.parametrize("B,C,H,N", [(64, 768, 12, 197), (5, 128, 2, 197), (3, 256, 4, 64), (16, 1024, 16, 197), (7, 384, 6, 200)])
-def test_vit_fused_single_launch_matches_three_launch_path(B, C, H, N, monkeypatch):
-    """The default path: the whole forward as ONE launch (phases chained by dependency counters).  Same arithmetic in the
-    same order as the three-launch path -> bit-identical output; repeated runs stay identical (no race)."""
+def test_vit_single_launch_kernels_match_three_launch_path(B, C, H, N, monkeypatch):
+    """The default path is ONE launch: the co-scheduled kernel (projection GEMMs under the softmax chain, two CTAs per SM)
+    where it qualifies, else the sequenced kernel (three phases back to back).  Same arithmetic in the same order as the
+    three-launch path -> bit-identical output from all three; repeated runs stay identical (no race)."""
     from pytorch_attention_b200 import _lib
     m, x = _fresh(C, H, B, N, 11, qkv_bias=(C == 128))
     m = m.cuda()
     if C == 384:
-        m.out_dtype = torch.float32        # fp32 y: the staging area holds fewer sub-tiles, two of the four epilogue sets idle
+        m.out_dtype = torch.float32        # fp32 y: sequenced kernel only (the co-scheduled one stores 16-bit rows)
     xg = x.cuda()
-    with torch.no_grad():
-        monkeypatch.setenv("PA_VIT_FUSED", "0")
-        n0 = _lib.launch_count()
-        y3 = m(xg)
-        assert _lib.launch_count() - n0 == 3
-        monkeypatch.setenv("PA_VIT_FUSED", "1")
-        n0 = _lib.launch_count()
-        y1 = m(xg)
-        assert _lib.launch_count() - n0 == 1
-        for _ in range(5):
-            assert torch.equal(m(xg), y1)
-        monkeypatch.delenv("PA_VIT_FUSED")
-    assert torch.equal(y1, y3)
+    try:
+        with torch.no_grad():
+            _setenv(monkeypatch, PA_VIT_FUSED=0, PA_VIT_COSCHED=0)
+            n0 = _lib.launch_count()
+            y3 = m(xg)
+            assert _lib.launch_count() - n0 == 3
+            _setenv(monkeypatch, PA_VIT_FUSED=1, PA_VIT_COSCHED=0)
+            n0 = _lib.launch_count()
+            y1 = m(xg)
+            assert _lib.launch_count() - n0 == 1
+            for _ in range(5):
+                assert torch.equal(m(xg), y1)
+            assert torch.equal(y1, y3)
+            if C != 384:
+                _setenv(monkeypatch, PA_VIT_FUSED=None, PA_VIT_COSCHED=1)
+                n0 = _lib.launch_count()
+                yc = m(xg)
+                assert _lib.launch_count() - n0 == 1
+                for _ in range(5):
+                    assert torch.equal(m(xg), yc)
+                assert torch.equal(yc, y3)
+            else:
+                _setenv(monkeypatch, PA_VIT_FUSED=None, PA_VIT_COSCHED=1)
+                with pytest.raises(ValueError):
+                    m(xg)                       # required but not applicable: an explicit error, never a silent switch
+            _setenv(monkeypatch, PA_VIT_FUSED=None, PA_VIT_COSCHED=None)
+            n0 = _lib.launch_count()
+            yd = m(xg)                          # default selection
+            assert _lib.launch_count() - n0 == 1
+            assert torch.equal(yd, y3)
+    finally:
+        _setenv(monkeypatch, PA_VIT_FUSED=None, PA_VIT_COSCHED=None)
     if B <= 5:
         sd = {k: v.float().cpu() for k, v in m.state_dict().items()}
         ref = vit_attention(x.float(), sd["qkv.weight"], sd.get("qkv.bias"), sd["proj.weight"], sd["proj.bias"], H)
         assert rel_fro(y1.float().cpu(), ref) < TOL
+
+
+def test_vit_co_scheduled_kernel_inside_cuda_graph_and_second_stream():
+    """The co-scheduled kernel establishes residency once with a probe launch + stream sync, which cannot run inside a
+    capture: the first capture after library load must still work (that call takes the sequenced kernel) and replays of
+    later captures must reproduce the eager result."""
+    m, x = _fresh(256, 4, 6, 197, 3)
+    m = m.cuda()
+    xg = x.cuda()
+    with torch.no_grad():
+        y0 = m(xg)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            m(xg)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                yg = m(xg)
+        torch.cuda.current_stream().wait_stream(s)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(yg, y0)

@@ -2,6 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from pytorch_attention_b200 import _lib
 from pytorch_attention_b200 import ops
 
 def timed(fn, reps=20):
@@ -25,6 +26,7 @@ q, k, v = [t.view(B, N, H, 64).permute(0, 2, 1, 3).float() for t in qkv.split(C,
 ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).permute(0, 2, 1, 3).reshape(B, N, C)
 for dbg in (0,):
     os.environ["PA_ATTN_DEBUG"] = str(dbg)
+    _lib.reload_env()
     fn = lambda: ops.attn_core(qkv, qkv, H, 0.125, 0, C, 2 * C, out=out)
     us = timed(fn)
     err = ((out.float() - ref).norm() / ref.norm()).item()

@@ -41,11 +41,31 @@ def graph_time(fn, reps=20):
     return a.elapsed_time(b) / reps * 1e3
 
 
+_collected = None     # collect(): lines are gathered instead of printed
+
+
 def emit(**kw):
+    if _collected is not None:
+        _collected.append(kw)
+        return
     line = json.dumps(kw)
     print(line, flush=True)
     with open(os.path.join(OUT, "configs.jsonl"), "a") as f:
         f.write(line + "\n")
+
+
+REPS = 20
+
+
+def collect(reps=20):
+    """All configurations as a list of dicts (bench.py's `other_configs` key)."""
+    global _collected, REPS
+    _collected, REPS = [], reps
+    try:
+        main()
+        return _collected
+    finally:
+        _collected = None
 
 
 def run(name, mod, x, call, tokens, flops, launches_expected=None):
@@ -55,7 +75,7 @@ def run(name, mod, x, call, tokens, flops, launches_expected=None):
         y = call(mod, x)
         torch.cuda.synchronize()
         n1 = _lib.launch_count()
-        us = graph_time(lambda: call(mod, x))
+        us = graph_time(lambda: call(mod, x), REPS)
     emit(config=name, us=round(us, 2), tokens_per_s=round(tokens / us * 1e6), tflops=round(flops / us / 1e6, 1),
          frac_of_measured_peak=round(flops / us / 1e6 / PEAK, 3), launches=n1 - n0, out_shape=list(y.shape))
 

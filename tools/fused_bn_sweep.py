@@ -2,6 +2,8 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+os.environ["PA_VIT_COSCHED"] = "0"   # sweep the sequenced kernel
+from pytorch_attention_b200 import _lib
 import pytorch_attention_b200 as pa
 
 def graph_time(fn, reps=30):
@@ -24,6 +26,7 @@ for C, H in ((768, 12), (1024, 16)):
         for bn1 in (256, 192):
             for bn2 in (256, 192):
                 os.environ["PA_FUSED_BN1"], os.environ["PA_FUSED_BN2"] = str(bn1), str(bn2)
+                _lib.reload_env()
                 print(f"C={C}: qkv tiles 256x{bn1}, proj tiles 256x{bn2}: {graph_time(lambda: m(x)):7.2f} us")
-        os.environ.pop("PA_FUSED_BN1"); os.environ.pop("PA_FUSED_BN2")
+        os.environ.pop("PA_FUSED_BN1"); os.environ.pop("PA_FUSED_BN2"); _lib.reload_env()
         print(f"C={C}: host cost model's choice: {graph_time(lambda: m(x)):7.2f} us")

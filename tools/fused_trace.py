@@ -1,6 +1,7 @@
 """Phase timeline of CTA 0 of the fused single-launch ViT kernel (clock64 stamps per tile/item, globaltimer per phase)."""
 import sys, os, ctypes
 os.environ["PA_VIT_FUSED"] = "1"
+os.environ["PA_VIT_COSCHED"] = "0"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import pytorch_attention_b200 as pa

@@ -43,6 +43,7 @@ with torch.no_grad():
     torch.cuda.synchronize()
     print(f"pa_vit_fwd alone (ctypes call, fused launch), host time: {(t1 - t0) / 300 * 1e6:.1f} us")
     os.environ["PA_VIT_FUSED"] = "0"
+    lib.pa_reload_env()
     for _ in range(5): lib.pa_vit_fwd(ctypes.byref(a), wsp, n, st)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
