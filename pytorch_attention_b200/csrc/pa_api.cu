@@ -1,5 +1,6 @@
 // pa_api.cu — C-ABI entry points of libpa_b200.so (see include/pa_b200.h).
 #include "pa_attn.cuh"
+#include "pa_attn_wide.cuh"
 #include "pa_gemm.cuh"
 #include "pa_fused.cuh"
 #include "pa_cosched.cuh"
@@ -307,7 +308,7 @@ struct AttnPlan {
 int attn_prepare(const AttnLaunch& a, AttnPlan* plan) {
   CUtensorMap& tq = plan->tq; CUtensorMap& tk = plan->tk; CUtensorMap& tv = plan->tv; CUtensorMap& to = plan->to;
   AttnParams& p = plan->p;
-  if (a.hd != 64 && a.hd != 32) return fail(PA_ERR_UNSUPPORTED, "attention core: head_dim %d unsupported (64 or 32)", a.hd);
+  if (a.hd != 64 && a.hd != 32) return fail(PA_ERR_UNSUPPORTED, "attention core: head_dim %d unsupported (32, 64, 96, 128, 160, 192)", a.hd);
   if (!(a.scale > 0.f)) return fail(PA_ERR_UNSUPPORTED, "attention core: scale must be > 0");
   if (a.ldo % 8 || a.o_col0 % 8 || a.o_group % 8 || (reinterpret_cast<uintptr_t>(a.o) & 15))
     return fail(PA_ERR_MISALIGNED, "attention core: output pitch/offset must be multiples of 8 elements");
@@ -396,7 +397,64 @@ int attn_prepare(const AttnLaunch& a, AttnPlan* plan) {
   return PA_OK;
 }
 
+// head dims 96 / 128 / 160 / 192: pa_attn_wide.cuh (panelled operands, 64-key blocks, online softmax, 2 CTAs per SM)
+template <int HD>
+int launch_attn_wide(const AttnLaunch& a, cudaStream_t st) {
+  using Cfg = AttnWideCfg<HD>;
+  int rc;
+  CUtensorMap tq, tk, tv;
+  const TmapSwizzle swz = Cfg::W == 64 ? TM_SWZ_128 : TM_SWZ_64;
+  {
+    uint64_t dims[3] = {(uint64_t)a.ldq, (uint64_t)a.n_q, (uint64_t)a.G};
+    uint64_t str[2] = {(uint64_t)a.ldq * 2, (uint64_t)a.q_group * 2};
+    uint32_t box[3] = {(uint32_t)Cfg::W, 128, 1};
+    if ((rc = make_tmap_16b(&tq, PA_DTYPE_F16, a.q, 3, dims, str, box, swz))) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)a.ldk, (uint64_t)a.n_k, (uint64_t)a.G};
+    uint64_t str[2] = {(uint64_t)a.ldk * 2, (uint64_t)a.k_group * 2};
+    uint32_t box[3] = {(uint32_t)Cfg::W, (uint32_t)AW_KB, 1};
+    if ((rc = make_tmap_16b(&tk, PA_DTYPE_F16, a.k, 3, dims, str, box, swz))) return rc;
+    if ((rc = make_tmap_16b(&tv, PA_DTYPE_F16, a.v, 3, dims, str, box, swz))) return rc;
+  }
+  AttnWideParams p = {};
+  p.G = a.G; p.H = a.H; p.n_q = a.n_q; p.n_k = a.n_k;
+  p.nkb = (a.n_k + AW_KB - 1) / AW_KB;
+  p.q_tiles = (a.n_q + 127) / 128;
+  p.units = a.G * a.H * p.q_tiles;
+  p.q_col0 = a.q_col0; p.k_col0 = a.k_col0; p.v_col0 = a.v_col0;
+  p.O = a.o; p.ldo = a.ldo; p.o_group = a.o_group; p.o_col0 = a.o_col0;
+  p.scale_log2e = a.scale * 1.4426950408889634f;
+  p.idesc_s = make_idesc(128, AW_KB, PA_F16, PA_F16, 0, 0);
+  p.idesc_o = make_idesc(128, Cfg::W, PA_F16, PA_F16, 0, 1);
+  static SmemAttr smem_attr;
+  if ((rc = smem_attr.ensure(attn_wide_kernel<HD>, Cfg::SMEM_BYTES))) return rc;
+  const int cap = 2 * num_sms();
+  const int grid = p.units < cap ? p.units : cap;
+  attn_wide_kernel<HD><<<grid, AW_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  return PA_OK;
+}
+
+inline bool attn_wide_hd(int hd) { return hd == 96 || hd == 128 || hd == 160 || hd == 192; }
+inline bool attn_hd_ok(int hd) { return hd == 32 || hd == 64 || attn_wide_hd(hd); }
+
 int attn_launch(const AttnLaunch& a, cudaStream_t st) {
+  if (attn_wide_hd(a.hd)) {
+    if (a.windowed) return fail(PA_ERR_UNSUPPORTED, "windowed attention: head_dim %d unsupported (32 or 64)", a.hd);
+    if (!(a.scale > 0.f)) return fail(PA_ERR_UNSUPPORTED, "attention core: scale must be > 0");
+    if (a.ldo % 8 || a.o_col0 % 8 || a.o_group % 8 || (reinterpret_cast<uintptr_t>(a.o) & 15))
+      return fail(PA_ERR_MISALIGNED, "attention core: output pitch/offset must be multiples of 8 elements");
+    int rc = current_device_check();
+    if (rc) return rc;
+    switch (a.hd) {
+      case 96: return launch_attn_wide<96>(a, st);
+      case 128: return launch_attn_wide<128>(a, st);
+      case 160: return launch_attn_wide<160>(a, st);
+      default: return launch_attn_wide<192>(a, st);
+    }
+  }
   AttnPlan plan;
   int rc = attn_prepare(a, &plan);
   if (rc) return rc;
@@ -555,7 +613,7 @@ static int vit_check(const pa_vit_args* a) {
   if (!a) return fail(PA_ERR_NULL, "pa_vit: args is NULL");
   if (a->B <= 0 || a->N <= 0 || a->C <= 0 || a->H <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_vit: B,N,C,H must be positive");
   if (a->C % a->H != 0) return fail(PA_ERR_BAD_SHAPE, "pa_vit: dim %d not divisible by num_heads %d (ViT.py:70)", a->C, a->H);
-  if (a->C / a->H != 64) return fail(PA_ERR_UNSUPPORTED, "pa_vit: head_dim %d unsupported (64 only)", a->C / a->H);
+  if (!attn_hd_ok(a->C / a->H)) return fail(PA_ERR_UNSUPPORTED, "pa_vit: head_dim %d unsupported (32, 64, 96, 128, 160, 192)", a->C / a->H);
   if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "pa_vit: dtype must be fp16/bf16");
   return PA_OK;
 }
@@ -593,8 +651,10 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
   //      takes an error instead of a silent switch; PA_VIT_COSCHED=0 / 1 never / always takes the co-scheduled kernel.
   const bool fused_forced = ev.vit_fused > 0 || ev.vit_cosched > 0;
   const bool fused_wanted = ev.vit_fused != 0;
-  bool fused_ok = fused_wanted && a->N <= 256;
-  if (fused_forced && !fused_ok) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(single launch): N=%d > 256 needs several key blocks", a->N);
+  const int hd = C / a->H;
+  bool fused_ok = fused_wanted && a->N <= 256 && hd == 64;
+  if (fused_forced && !fused_ok)
+    return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(single launch): needs N <= 256 (one key block) and 64-wide heads; got N=%d, head_dim=%d", a->N, hd);
   if (fused_ok) {
     if ((rc = current_device_check())) return rc;
     pa_gemm_args g1 = {};
@@ -725,7 +785,7 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
   if ((rc = linear(a->x, a->dtype, C, a->qkv_weight, a->dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
   // 2. per (b,h): softmax(q k^T scale) v       (ViT.py:83-86), O as [B*N, C] with column h*64+d
   AttnLaunch at = {};
-  at.hd = 64; at.G = a->B; at.H = a->H; at.n_q = a->N; at.n_k = a->N;
+  at.hd = hd; at.G = a->B; at.H = a->H; at.n_q = a->N; at.n_k = a->N;
   at.q = qkv; at.ldq = 3 * C; at.q_group = (long long)a->N * 3 * C; at.q_col0 = 0;
   at.k = qkv; at.v = qkv; at.ldk = 3 * C; at.k_group = (long long)a->N * 3 * C; at.k_col0 = C; at.v_col0 = 2 * C;
   at.o = obuf; at.ldo = C; at.o_group = (long long)a->N * C; at.o_col0 = 0;
@@ -771,7 +831,7 @@ static int pvt_check(const pa_pvt_args* a) {
   if (!a) return fail(PA_ERR_NULL, "pa_pvt: args is NULL");
   if (a->B <= 0 || a->C <= 0 || a->H <= 0 || a->Himg <= 0 || a->Wimg <= 0 || a->sr <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: sizes must be positive");
   if (a->C % a->H != 0) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: dim %d not divisible by num_heads %d (pvt.py:56)", a->C, a->H);
-  if (a->C / a->H != 64) return fail(PA_ERR_UNSUPPORTED, "pa_pvt: head_dim %d unsupported (64 only)", a->C / a->H);
+  if (!attn_hd_ok(a->C / a->H)) return fail(PA_ERR_UNSUPPORTED, "pa_pvt: head_dim %d unsupported (32, 64, 96, 128, 160, 192)", a->C / a->H);
   if (a->N != a->Himg * a->Wimg) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: N=%d != H*W=%d*%d", a->N, a->Himg, a->Wimg);
   if (a->C % 8) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: dim must be a multiple of 8");
   if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "pa_pvt: dtype must be fp16/bf16");
@@ -819,7 +879,7 @@ int pa_pvt_fwd(const pa_pvt_args* a, void* workspace, size_t workspace_bytes, vo
   if ((rc = linear(a->x, a->dtype, C, a->q_weight, a->dtype, a->q_bias, qb, PA_DTYPE_F16, C, rows, C, C, st))) return rc;
   if ((rc = linear(kv_in, kv_dtype, C, a->kv_weight, kv_dtype, a->kv_bias, kv, PA_DTYPE_F16, 2 * C, mrows, 2 * C, C, st))) return rc;
   AttnLaunch at = {};
-  at.hd = 64; at.G = a->B; at.H = a->H; at.n_q = a->N; at.n_k = M;
+  at.hd = C / a->H; at.G = a->B; at.H = a->H; at.n_q = a->N; at.n_k = M;
   at.q = qb; at.ldq = C; at.q_group = (long long)a->N * C; at.q_col0 = 0;
   at.k = kv; at.v = kv; at.ldk = 2 * C; at.k_group = (long long)M * 2 * C; at.k_col0 = 0; at.v_col0 = C;
   at.o = ob; at.ldo = C; at.o_group = (long long)a->N * C; at.o_col0 = 0;
@@ -833,7 +893,7 @@ static int cvt_check(const pa_cvt_args* a) {
   if (!a) return fail(PA_ERR_NULL, "pa_cvt: args is NULL");
   if (a->B <= 0 || a->C <= 0 || a->H <= 0 || a->Himg <= 0 || a->Wimg <= 0 || a->ks <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_cvt: sizes must be positive");
   if (a->C % a->H != 0) return fail(PA_ERR_BAD_SHAPE, "pa_cvt: dim %d not divisible by num_heads %d (cvt.py:51)", a->C, a->H);
-  if (a->C / a->H != 64) return fail(PA_ERR_UNSUPPORTED, "pa_cvt: head_dim %d unsupported (64 only)", a->C / a->H);
+  if (!attn_hd_ok(a->C / a->H)) return fail(PA_ERR_UNSUPPORTED, "pa_cvt: head_dim %d unsupported (32, 64, 96, 128, 160, 192)", a->C / a->H);
   if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "pa_cvt: dtype must be fp16/bf16");
   return PA_OK;
 }
@@ -870,7 +930,7 @@ int pa_cvt_fwd(const pa_cvt_args* a, void* workspace, size_t workspace_bytes, vo
   // 1x1 conv == linear over channels   (cvt.py:58), rows ordered (s,h,d) as ViT (cvt.py:66)
   if ((rc = linear(tok, PA_DTYPE_F16, C, a->qkv_weight, PA_DTYPE_F16, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
   AttnLaunch at = {};
-  at.hd = 64; at.G = a->B; at.H = a->H; at.n_q = HW; at.n_k = HW;
+  at.hd = C / a->H; at.G = a->B; at.H = a->H; at.n_q = HW; at.n_k = HW;
   at.q = qkv; at.ldq = 3 * C; at.q_group = (long long)HW * 3 * C; at.q_col0 = 0;
   at.k = qkv; at.v = qkv; at.ldk = 3 * C; at.k_group = (long long)HW * 3 * C; at.k_col0 = C; at.v_col0 = 2 * C;
   at.o = ob; at.ldo = C; at.o_group = (long long)HW * C; at.o_col0 = 0;

@@ -39,8 +39,10 @@ def test_vit_argument_validation_without_gpu():
     a.B, a.N, a.C, a.H = 2, 197, 768, 5          # 768 % 5 != 0  (ViT.py:70 assert)
     assert lib.pa_vit_fwd(C.byref(a), None, 0, None) == L.PA_ERR_BAD_SHAPE
     assert b"divisible" in lib.pa_last_error()
-    a.H = 6                                       # head_dim 128 unsupported
+    a.H = 16                                      # head_dim 48: not a multiple of 32
     assert lib.pa_vit_fwd(C.byref(a), None, 0, None) == L.PA_ERR_UNSUPPORTED
+    a.H = 4                                       # head_dim 192 (the reference's default, ViT.py:67) is served
+    assert lib.pa_vit_workspace_bytes(C.byref(a)) > 0
     a.H = 12
     assert lib.pa_vit_workspace_bytes(C.byref(a)) >= 2 * 197 * 768 * 2 * 4
     assert lib.pa_vit_fwd(C.byref(a), None, 0, None) == L.PA_ERR_NULL   # x/weights NULL

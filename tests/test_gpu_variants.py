@@ -61,6 +61,11 @@ ORACLE_CASES = {
     # XCiT at ViT-B-like width
     "xca_768": dict(variant="xca", ctor=dict(dim=768, num_heads=12), x=(2, 196, 768)),
     "classattn_768": dict(variant="class_attn", ctor=dict(dim=768, num_heads=12), x=(2, 197, 768)),
+    # constructor defaults of the reference classes that do not give 64-wide heads: pvt.Attention(dim, num_heads=8) at the
+    # zoo's 1024-wide heads -> 128; cvt.Attention(dim=768, num_heads=8) -> 96; 32-wide heads through both entry points
+    "pvt_hd128": dict(variant="pvt", ctor=dict(dim=512, num_heads=4, sr_ratio=2), x=(2, 196, 512), hw=(14, 14)),
+    "pvt_hd32": dict(variant="pvt", ctor=dict(dim=128, num_heads=4, sr_ratio=1), x=(2, 196, 128), hw=(14, 14)),
+    "cvt_hd96": dict(variant="cvt", ctor=dict(dim=192, num_heads=2), x=(2, 192, 14, 14)),
     # the zoo's own XCiT configuration (xcit_nano_12_p16, xcit.py:393: dim 128, 4 heads -> 32-wide heads, A is 32 x 32)
     "xca_nano_hd32": dict(variant="xca", ctor=dict(dim=128, num_heads=4), x=(3, 196, 128)),
     "classattn_nano_hd32": dict(variant="class_attn", ctor=dict(dim=128, num_heads=4), x=(3, 197, 128)),

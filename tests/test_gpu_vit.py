@@ -204,3 +204,41 @@ def test_vit_co_scheduled_kernel_inside_cuda_graph_and_second_stream():
             g.replay()
         torch.cuda.synchronize()
         assert torch.equal(yg, y0)
+
+
+@pytest.mark.parametrize("C,H,B,N", [(768, 4, 3, 197),      # the reference's DEFAULT: ViT.Attention(dim=768, num_heads=4) -> head_dim 192 (ViT.py:67, 121-127)
+                                     (512, 4, 2, 197),      # head_dim 128
+                                     (384, 4, 2, 130),      # head_dim 96 (three 32-wide panels)
+                                     (640, 4, 2, 64),       # head_dim 160, a single key block
+                                     (256, 8, 2, 197),      # head_dim 32 through the ViT entry point
+                                     (384, 2, 1, 600)])     # head_dim 192, ten key blocks
+def test_vit_other_head_dims_vs_oracle(C, H, B, N):
+    """Head dims beyond 64 run the panelled core (pa_attn_wide.cuh): three launches, same 1e-3 bar against the oracle."""
+    from pytorch_attention_b200 import _lib
+    m, x = _fresh(C, H, B, N, 21, qkv_bias=(C == 512))
+    sd = {k: v.float() for k, v in m.state_dict().items()}
+    ref = vit_attention(x.float(), sd["qkv.weight"], sd.get("qkv.bias"), sd["proj.weight"], sd["proj.bias"], H)
+    m = m.cuda()
+    with torch.no_grad():
+        n0 = _lib.launch_count()
+        y = m(x.cuda())
+        assert _lib.launch_count() - n0 == 3
+        assert torch.equal(m(x.cuda()), y)
+    assert rel_fro(y.float().cpu(), ref) < TOL and rel_max(y.float().cpu(), ref) < TOL
+
+
+def test_vit_reference_default_constructor_runs():
+    """`ViT.Attention(768)` with every constructor default (num_heads=4, no qkv bias) -- the configuration the reference's own
+    VisionTransformer() uses (README.md:331-334) -- at the BASELINE batch."""
+    import pytorch_attention_b200 as pa
+    torch.manual_seed(5)
+    m = pa.ViTAttention(768).eval().half().cuda()
+    assert m.num_heads == 4
+    x = torch.randn(64, 197, 768, device="cuda").half()
+    with torch.no_grad():
+        y = m(x)
+        perm = torch.randperm(64, device="cuda")
+        assert torch.equal(m(x[perm]), y[perm])          # images are independent: batch permutation is bit-exact
+        sd = {k: v.float().cpu() for k, v in m.state_dict().items()}
+        ref = vit_attention(x[:2].float().cpu(), sd["qkv.weight"], None, sd["proj.weight"], sd["proj.bias"], 4)
+    assert rel_fro(y[:2].float().cpu(), ref) < TOL
