@@ -73,6 +73,9 @@ typedef struct {
   int cluster;                       /* 0 = auto; 1/2/4: CTAs per cluster sharing the B tile by TMA multicast; -2: CTA pairs (tcgen05 cta_group::2) */
 } pa_gemm_args;
 int pa_gemm_tn(const pa_gemm_args* a, void* stream);
+/* dst[i] = (fp16 | bf16) src[i], i < n: the cast in front of a forward when the caller's activations are fp32 (the reference's
+ * forward is fp32 in / fp32 out, ViT.py:79; the drop-ins' opt-in `fp32_input` mode).  Both buffers 16-byte aligned. */
+int pa_cast_f32(const float* src, void* dst, long long n, int out_dtype, void* stream);
 /* debug aid: CTA 0 of later GEMM launches writes per-tile clock64 stamps into this device buffer (>= 4 KiB); NULL turns it off */
 void pa_debug_set_gemm_trace(void* device_buffer);
 

@@ -16,6 +16,11 @@ GOLDEN_CASES = {
     # ViT.Attention(dim, num_heads, qkv_bias)            ViT.py:67-89
     "vit_b2_n197_c128_h2": dict(variant="vit", ctor=dict(dim=128, num_heads=2), x=(2, 197, 128)),
     "vit_b3_n50_c192_h3_bias": dict(variant="vit", ctor=dict(dim=192, num_heads=3, qkv_bias=True), x=(3, 50, 192)),
+    # 192-wide heads (the reference's default ViT.Attention(num_heads=4) at dim 768 has them; here at dim 384 to keep the file small)
+    "vit_b2_n197_c384_h2_hd192": dict(variant="vit", ctor=dict(dim=384, num_heads=2), x=(2, 197, 384)),
+    # setr.Attention(dim, num_heads=8) setr.py:50-72 and moat.Attention(dim, num_heads=8) moat.py:62-84: ViT's math
+    "setr_b2_n100_c256_default_heads": dict(variant="setr", ctor=dict(dim=256), x=(2, 100, 256)),
+    "moat_b2_n196_c512_default_heads_bias": dict(variant="moat", ctor=dict(dim=512, qkv_bias=True), x=(2, 196, 512)),
     # pvt.Attention(dim, num_heads, sr_ratio)            pvt.py:52-91
     "pvt_b2_16x16_c128_h2_sr4": dict(variant="pvt", ctor=dict(dim=128, num_heads=2, sr_ratio=4), x=(2, 256, 128), hw=(16, 16)),
     "pvt_b2_8x8_c128_h2_sr1_bias": dict(variant="pvt", ctor=dict(dim=128, num_heads=2, sr_ratio=1, qkv_bias=True), x=(2, 64, 128), hw=(8, 8)),
@@ -35,6 +40,8 @@ GOLDEN_CASES = {
 
 _REF_CLASS = {
     "vit": ("ViT", "Attention"),
+    "setr": ("setr", "Attention"),
+    "moat": ("moat", "Attention"),
     "pvt": ("pvt", "Attention"),
     "cvt": ("cvt", "Attention"),
     "lepe": ("cswin", "LePEAttention"),
@@ -87,7 +94,23 @@ def make_inputs(spec, seed=0):
 def load_reference(ref_path):
     if ref_path not in sys.path:
         sys.path.insert(0, ref_path)
-    return {m: importlib.import_module(m) for m in ("ViT", "pvt", "cvt", "cswin", "xcit")}
+    return {m: importlib.import_module(m) for m in ("ViT", "pvt", "cvt", "cswin", "xcit", "moat")}
+
+
+def load_reference_class(ref_path, module, cls):
+    """The reference class object.  ``setr.py`` builds and runs a whole SETR model at import time (setr.py:131-134), so for
+    that file only the module's imports and its own class definitions are executed -- still the reference's code, read
+    from where it lies, just without the module-level demo."""
+    if module != "setr":
+        return getattr(load_reference(ref_path)[module], cls)
+    import ast
+    import os
+    src = open(os.path.join(ref_path, module + ".py")).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom, ast.ClassDef, ast.FunctionDef))]
+    ns = {"__name__": "reference_" + module}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), os.path.join(ref_path, module + ".py"), "exec"), ns)
+    return ns[cls]
 
 
 def reference_forward(spec, mod, x):
@@ -117,10 +140,9 @@ def cswin_block_attention_half_reference(blk, x):
 
 
 def build_reference_case(spec, ref_path, seed=0):
-    mods = load_reference(ref_path)
     modname, clsname = _REF_CLASS[spec["variant"]]
     torch.manual_seed(seed)
-    mod = getattr(mods[modname], clsname)(**spec["ctor"]).eval()
+    mod = load_reference_class(ref_path, modname, clsname)(**spec["ctor"]).eval()
     randomise_module_(mod, seed + 7)
     inputs = make_inputs(spec, seed)
     y = reference_forward(spec, mod, inputs["x"]).float()
@@ -138,9 +160,10 @@ def run_oracle_case(spec, inputs, params, dtype=torch.float32):
     c = spec["ctor"]
     P = {k: (t.to(dtype) if t.is_floating_point() else t) for k, t in params.items()}
     x = inputs["x"].to(dtype)
-    if v == "vit":
+    if v in ("vit", "setr", "moat"):
+        # setr.py:62-72 and moat.py:74-84 restate ViT.py:79-89; their constructor default is 8 heads
         return A.vit_attention(x, P["qkv.weight"], P.get("qkv.bias"), P["proj.weight"], P["proj.bias"],
-                               c["num_heads"])
+                               c.get("num_heads", 4 if v == "vit" else 8))
     if v == "pvt":
         kw = _kw(P, "q.weight", "q.bias", "k.weight", "k.bias", "v.weight", "v.bias", "proj.weight", "proj.bias",
                  "sr.0.weight", "sr.0.bias", "sr.1.weight", "sr.1.bias", "sr.1.running_mean", "sr.1.running_var")

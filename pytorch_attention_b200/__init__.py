@@ -1,5 +1,5 @@
 """pytorch_attention_b200 — B200-native (sm_100a) attention forward, drop-in for the attention modules of
-changzy00/pytorch-attention's vision_transformers/ (ViT, PVT, CvT, CSWin, XCiT).
+changzy00/pytorch-attention's vision_transformers/ (ViT, PVT, CvT, CSWin, XCiT, and the ViT-identical SETR / MOAT attention).
 
 Python here is plumbing only (module state, device memory, streams); all arithmetic runs in the hand-written
 CUDA library ``lib/libpa_b200.so`` behind the C ABI declared in ``include/pa_b200.h``.  The sub-modules mirror
@@ -7,12 +7,12 @@ the reference's file names so that ``from pytorch_attention_b200.pvt import Atte
 ``from pvt import Attention``.
 """
 from . import _lib, ops  # noqa: F401
-from . import vit, pvt, cvt, cswin, xcit  # noqa: F401
+from . import vit, pvt, cvt, cswin, xcit, setr, moat  # noqa: F401
 from .vit import Attention as ViTAttention  # noqa: F401
 from .pvt import Attention as PVTAttention  # noqa: F401
 from .cvt import Attention as CvTAttention  # noqa: F401
 from .cswin import LePEAttention, CSWinBlock  # noqa: F401
 from .xcit import XCA, ClassAttention  # noqa: F401
 
-__all__ = ["ops", "vit", "pvt", "cvt", "cswin", "xcit", "ViTAttention", "PVTAttention", "CvTAttention",
+__all__ = ["ops", "vit", "pvt", "cvt", "cswin", "xcit", "setr", "moat", "ViTAttention", "PVTAttention", "CvTAttention",
            "LePEAttention", "CSWinBlock", "XCA", "ClassAttention"]

@@ -87,6 +87,7 @@ SYMBOLS = {
     "pa_reload_env": (None, []),
     "pa_debug_cosched_occupancy": (_i, [_i, C.POINTER(_i)]),
     "pa_gemm_tn": (_i, [C.POINTER(GemmArgs), _vp]),
+    "pa_cast_f32": (_i, [_vp, _vp, _ll, _i, _vp]),
     "pa_debug_set_gemm_trace": (None, [_vp]),
     "pa_attn_core": (_i, [C.POINTER(AttnArgs), _vp]),
     "pa_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitArgs)]),
@@ -128,6 +129,7 @@ def load():
         if _lib is not None:
             return _lib
         path = _build.LIB_PATH
+        stale_error = None
         if _build.is_stale():
             try:
                 _build.build_lib()
@@ -136,11 +138,26 @@ def load():
                     raise RuntimeError(
                         f"libpa_b200.so is not built ({path}) and could not be built: {e}. "
                         "This package has no CPU / PyTorch fallback.") from e
+                stale_error = e
         lib = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
-            fn = getattr(lib, name)   # AttributeError if the symbol is not exported
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:
+                raise RuntimeError(f"{path} does not export {name}: the library is older than the sources"
+                                   + (f" and the rebuild failed: {stale_error}" if stale_error else "")) from e
             fn.restype = res
             fn.argtypes = args
+        if stale_error is not None:
+            # an older library is in use although the sources are newer (e.g. the GPU box has no nvcc in PATH): say so, and
+            # refuse outright if its ABI version differs from the header this package was written against
+            import warnings
+            want = _build.header_version()
+            if want is not None and int(lib.pa_version()) != want:
+                raise RuntimeError(f"{path} reports ABI version {lib.pa_version()} but include/pa_b200.h declares {want}, "
+                                   f"and the rebuild failed: {stale_error}")
+            warnings.warn(f"libpa_b200.so is older than its sources and could not be rebuilt ({stale_error}); using it as is",
+                          RuntimeWarning)
         _lib = lib
         return lib
 

@@ -47,17 +47,41 @@ def is_stale():
 
 
 def build_lib(force=False, verbose=False):
-    """Compile csrc/*.cu into lib/libpa_b200.so.  Returns the library path."""
+    """Compile csrc/*.cu into lib/libpa_b200.so.  Returns the library path.
+
+    Safe with several processes (N torchrun ranks finding a stale library): the build runs under an exclusive file lock,
+    nvcc writes to a temporary name and the result is moved into place atomically, so nobody can dlopen a half-written
+    file; a rank that waited for the lock re-checks staleness and skips the compile."""
     if not force and not is_stale():
         return LIB_PATH
+    import fcntl
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():
+                return LIB_PATH                  # another process built it while we waited
+            tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
+
+
+def header_version():
+    """PA_VERSION of include/pa_b200.h (what a freshly built library reports from pa_version())."""
+    import re
+    with open(os.path.join(INCLUDE_DIR, "pa_b200.h")) as f:
+        m = re.search(r"#define\s+PA_VERSION\s+(\d+)", f.read())
+    return int(m.group(1)) if m else None
 
 
 if __name__ == "__main__":

@@ -308,7 +308,7 @@ struct AttnPlan {
 int attn_prepare(const AttnLaunch& a, AttnPlan* plan) {
   CUtensorMap& tq = plan->tq; CUtensorMap& tk = plan->tk; CUtensorMap& tv = plan->tv; CUtensorMap& to = plan->to;
   AttnParams& p = plan->p;
-  if (a.hd != 64 && a.hd != 32) return fail(PA_ERR_UNSUPPORTED, "attention core: head_dim %d unsupported (32, 64, 96, 128, 160, 192)", a.hd);
+  if (a.hd != 64 && a.hd != 32) return fail(PA_ERR_UNSUPPORTED, "attention core: head_dim %d unsupported (multiples of 16 from 32 to 192)", a.hd);
   if (!(a.scale > 0.f)) return fail(PA_ERR_UNSUPPORTED, "attention core: scale must be > 0");
   if (a.ldo % 8 || a.o_col0 % 8 || a.o_group % 8 || (reinterpret_cast<uintptr_t>(a.o) & 15))
     return fail(PA_ERR_MISALIGNED, "attention core: output pitch/offset must be multiples of 8 elements");
@@ -397,13 +397,13 @@ int attn_prepare(const AttnLaunch& a, AttnPlan* plan) {
   return PA_OK;
 }
 
-// head dims 96 / 128 / 160 / 192: pa_attn_wide.cuh (panelled operands, 64-key blocks, online softmax, 2 CTAs per SM)
+// head dims 48 / 80 / 96 / ... / 192 (multiples of 16 other than 32 and 64): pa_attn_wide.cuh (panelled operands, 64-key blocks, online softmax, 2 CTAs per SM)
 template <int HD>
 int launch_attn_wide(const AttnLaunch& a, cudaStream_t st) {
   using Cfg = AttnWideCfg<HD>;
   int rc;
   CUtensorMap tq, tk, tv;
-  const TmapSwizzle swz = Cfg::W == 64 ? TM_SWZ_128 : TM_SWZ_64;
+  const TmapSwizzle swz = Cfg::W == 64 ? TM_SWZ_128 : Cfg::W == 32 ? TM_SWZ_64 : TM_SWZ_32;
   {
     uint64_t dims[3] = {(uint64_t)a.ldq, (uint64_t)a.n_q, (uint64_t)a.G};
     uint64_t str[2] = {(uint64_t)a.ldq * 2, (uint64_t)a.q_group * 2};
@@ -437,7 +437,7 @@ int launch_attn_wide(const AttnLaunch& a, cudaStream_t st) {
   return PA_OK;
 }
 
-inline bool attn_wide_hd(int hd) { return hd == 96 || hd == 128 || hd == 160 || hd == 192; }
+inline bool attn_wide_hd(int hd) { return hd % 16 == 0 && hd >= 48 && hd <= 192 && hd != 64; }
 inline bool attn_hd_ok(int hd) { return hd == 32 || hd == 64 || attn_wide_hd(hd); }
 
 int attn_launch(const AttnLaunch& a, cudaStream_t st) {
@@ -449,9 +449,14 @@ int attn_launch(const AttnLaunch& a, cudaStream_t st) {
     int rc = current_device_check();
     if (rc) return rc;
     switch (a.hd) {
+      case 48: return launch_attn_wide<48>(a, st);
+      case 80: return launch_attn_wide<80>(a, st);
       case 96: return launch_attn_wide<96>(a, st);
+      case 112: return launch_attn_wide<112>(a, st);
       case 128: return launch_attn_wide<128>(a, st);
+      case 144: return launch_attn_wide<144>(a, st);
       case 160: return launch_attn_wide<160>(a, st);
+      case 176: return launch_attn_wide<176>(a, st);
       default: return launch_attn_wide<192>(a, st);
     }
   }
@@ -606,6 +611,24 @@ int pa_device_check(int device) {
 void pa_debug_set_gemm_trace(void* device_buffer) { g_gemm_trace = reinterpret_cast<long long*>(device_buffer); }
 
 int pa_gemm_tn(const pa_gemm_args* a, void* stream) { return gemm_impl(a, (cudaStream_t)stream); }
+
+int pa_cast_f32(const float* src, void* dst, long long n, int out_dtype, void* stream) {
+  if (!src || !dst) return fail(PA_ERR_NULL, "pa_cast_f32: src/dst must be non-NULL");
+  if (n < 0) return fail(PA_ERR_BAD_SHAPE, "pa_cast_f32: n must be >= 0");
+  if (out_dtype != PA_DTYPE_F16 && out_dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "pa_cast_f32: out_dtype must be fp16/bf16");
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return fail(PA_ERR_MISALIGNED, "pa_cast_f32: buffers must be 16-byte aligned");
+  int rc = current_device_check();
+  if (rc) return rc;
+  if (n == 0) return PA_OK;
+  const long long n8 = n / 8;
+  const int tail = (int)(n - n8 * 8);
+  cast_f32_to_16_kernel<<<grid_for(n8 > 0 ? n8 : 1, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(dst), n8, out_dtype == PA_DTYPE_BF16, src + n8 * 8,
+      reinterpret_cast<uint16_t*>(dst) + n8 * 8, tail);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  return PA_OK;
+}
 int pa_attn_core(const pa_attn_args* a, void* stream) { return attn_impl(a, (cudaStream_t)stream); }
 
 // ================================================================ ViT  (ViT.py:67-89)
@@ -613,7 +636,7 @@ static int vit_check(const pa_vit_args* a) {
   if (!a) return fail(PA_ERR_NULL, "pa_vit: args is NULL");
   if (a->B <= 0 || a->N <= 0 || a->C <= 0 || a->H <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_vit: B,N,C,H must be positive");
   if (a->C % a->H != 0) return fail(PA_ERR_BAD_SHAPE, "pa_vit: dim %d not divisible by num_heads %d (ViT.py:70)", a->C, a->H);
-  if (!attn_hd_ok(a->C / a->H)) return fail(PA_ERR_UNSUPPORTED, "pa_vit: head_dim %d unsupported (32, 64, 96, 128, 160, 192)", a->C / a->H);
+  if (!attn_hd_ok(a->C / a->H)) return fail(PA_ERR_UNSUPPORTED, "pa_vit: head_dim %d unsupported (multiples of 16 from 32 to 192)", a->C / a->H);
   if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "pa_vit: dtype must be fp16/bf16");
   return PA_OK;
 }
@@ -831,7 +854,7 @@ static int pvt_check(const pa_pvt_args* a) {
   if (!a) return fail(PA_ERR_NULL, "pa_pvt: args is NULL");
   if (a->B <= 0 || a->C <= 0 || a->H <= 0 || a->Himg <= 0 || a->Wimg <= 0 || a->sr <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: sizes must be positive");
   if (a->C % a->H != 0) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: dim %d not divisible by num_heads %d (pvt.py:56)", a->C, a->H);
-  if (!attn_hd_ok(a->C / a->H)) return fail(PA_ERR_UNSUPPORTED, "pa_pvt: head_dim %d unsupported (32, 64, 96, 128, 160, 192)", a->C / a->H);
+  if (!attn_hd_ok(a->C / a->H)) return fail(PA_ERR_UNSUPPORTED, "pa_pvt: head_dim %d unsupported (multiples of 16 from 32 to 192)", a->C / a->H);
   if (a->N != a->Himg * a->Wimg) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: N=%d != H*W=%d*%d", a->N, a->Himg, a->Wimg);
   if (a->C % 8) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: dim must be a multiple of 8");
   if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "pa_pvt: dtype must be fp16/bf16");
@@ -893,7 +916,7 @@ static int cvt_check(const pa_cvt_args* a) {
   if (!a) return fail(PA_ERR_NULL, "pa_cvt: args is NULL");
   if (a->B <= 0 || a->C <= 0 || a->H <= 0 || a->Himg <= 0 || a->Wimg <= 0 || a->ks <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_cvt: sizes must be positive");
   if (a->C % a->H != 0) return fail(PA_ERR_BAD_SHAPE, "pa_cvt: dim %d not divisible by num_heads %d (cvt.py:51)", a->C, a->H);
-  if (!attn_hd_ok(a->C / a->H)) return fail(PA_ERR_UNSUPPORTED, "pa_cvt: head_dim %d unsupported (32, 64, 96, 128, 160, 192)", a->C / a->H);
+  if (!attn_hd_ok(a->C / a->H)) return fail(PA_ERR_UNSUPPORTED, "pa_cvt: head_dim %d unsupported (multiples of 16 from 32 to 192)", a->C / a->H);
   if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "pa_cvt: dtype must be fp16/bf16");
   return PA_OK;
 }

@@ -1,9 +1,10 @@
-// pa_attn_wide.cuh — softmax(Q K^T * scale) V for head dims the 64-wide core (pa_attn.cuh) does not take: 96, 128, 160, 192.
+// pa_attn_wide.cuh — softmax(Q K^T * scale) V for the head dims the 32/64-wide core (pa_attn.cuh) does not take: every multiple
+// of 16 up to 192 (48, 80, 96, 112, 128, 144, 160, 176, 192).
 // (The reference's own default ViT.Attention(dim=768, num_heads=4) has 192-wide heads: ViT.py:67, 121-127.)
 //
 // A head row of HD 16-bit values is wider than one swizzle atom, so Q / K / V tiles live in shared memory as NP = HD / W
-// column panels of W elements (W = 64 -> 128-byte swizzle, W = 32 -> 64-byte swizzle; 96 = 3 x 32, 160 = 5 x 32), one TMA
-// box per panel; the S MMA accumulates over the panels, the PV MMA writes one W-column group of O per panel.
+// column panels of W elements (W = 64 -> 128-byte swizzle, W = 32 -> 64-byte swizzle, W = 16 -> 32-byte swizzle; 96 = 3 x 32,
+// 48 = 3 x 16: the zoo's moat_0 has 48-wide heads, moat.py:144-146), one TMA box per panel; the S MMA accumulates over the panels, the PV MMA writes one W-column group of O per panel.
 // TMEM (256 columns, so two CTAs fit on an SM): S fp32 [0, 64) for one block of 64 keys, fp16 P written over it [0, 32),
 // O fp32 [64, 64 + HD) -- no aliasing, so HD = 192 fits exactly.  Keys are processed in blocks of 64 with an online softmax;
 // one thread owns one query row and keeps the whole S block in registers (64 values): a single TMEM read per score.
@@ -22,17 +23,18 @@ constexpr int AW_O_COL = 64;
 
 template <int HD>
 struct AttnWideCfg {
-  static constexpr int W = (HD % 64 == 0) ? 64 : 32;
+  static constexpr int W = (HD % 64 == 0) ? 64 : (HD % 32 == 0) ? 32 : 16;
   static constexpr int NP = HD / W;
   static constexpr int ROW_BYTES = W * 2;
   static constexpr int SBO = 8 * ROW_BYTES;
-  static constexpr uint64_t SWZ = (W == 64) ? PA_SWZ_128B : PA_SWZ_64B;
+  static constexpr uint64_t SWZ = (W == 64) ? PA_SWZ_128B : (W == 32) ? PA_SWZ_64B : PA_SWZ_32B;
+  static constexpr int OSTEP = (HD % 32 == 0) ? 32 : 16;          // O columns per TMEM round trip in the rescale / read-out loops
   static constexpr int Q_PANEL = 128 * ROW_BYTES;
   static constexpr int KV_PANEL = AW_KB * ROW_BYTES;
   static constexpr int V_KSTEP = 16 * ROW_BYTES / 16;
   static constexpr int Q_BYTES = NP * Q_PANEL, KV_BYTES = NP * KV_PANEL;
   static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_BYTES + 128 + 1024;
-  static_assert(HD % 32 == 0 && HD >= 32 && AW_O_COL + HD <= 256, "head_dim must be a multiple of 32, at most 192");
+  static_assert(HD % 16 == 0 && HD >= 16 && AW_O_COL + HD <= 256, "head_dim must be a multiple of 16, at most 192");
 };
 
 struct AttnWideParams {
@@ -207,13 +209,13 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait(o_full, (bc - 1) & 1);
           tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < HD; c += 32) {
-            uint32_t o[32];
-            tmem_ld32(t_row + AW_O_COL + c, o);
+          for (int c = 0; c < HD; c += Cfg::OSTEP) {
+            uint32_t o[Cfg::OSTEP];
+            if constexpr (Cfg::OSTEP == 32) tmem_ld32(t_row + AW_O_COL + c, o); else tmem_ld16(t_row + AW_O_COL + c, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32v(t_row + AW_O_COL + c, o);
+            for (int i = 0; i < Cfg::OSTEP; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            if constexpr (Cfg::OSTEP == 32) tmem_st32v(t_row + AW_O_COL + c, o); else tmem_st16(t_row + AW_O_COL + c, o);
           }
         }
         tmem_st32v(t_row, pk);
@@ -228,11 +230,11 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float inv = 1.f / l_run;
       uint16_t* dst = reinterpret_cast<uint16_t*>(p.O) + (long long)g * p.o_group + (long long)row * p.ldo + p.o_col0 + h * HD;
 #pragma unroll 1
-      for (int c = 0; c < HD; c += 32) {
-        uint32_t o[32];
-        tmem_ld32(t_row + AW_O_COL + c, o);
+      for (int c = 0; c < HD; c += Cfg::OSTEP) {
+        uint32_t o[Cfg::OSTEP];
+        if constexpr (Cfg::OSTEP == 32) tmem_ld32(t_row + AW_O_COL + c, o); else tmem_ld16(t_row + AW_O_COL + c, o);
         tmem_ld_wait();
-        if (c + 32 >= HD) {
+        if (c + Cfg::OSTEP >= HD) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(o_read);          // the next unit's first PV may overwrite O
@@ -240,7 +242,7 @@ attn_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (row < p.n_q) {
           uint4* d4 = reinterpret_cast<uint4*>(dst + c);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < Cfg::OSTEP / 8; ++i) {
             float f[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(o[8 * i + k]) * inv;

@@ -79,7 +79,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 tmap_encode_fn() {
 }
 
 // rank-N tiled map over a 16-bit tensor.  dims[0] is the contiguous dimension; strides (bytes) for dims 1..rank-1.
-enum TmapSwizzle { TM_SWZ_128 = 0, TM_SWZ_64 = 1 };
+enum TmapSwizzle { TM_SWZ_128 = 0, TM_SWZ_64 = 1, TM_SWZ_32 = 2 };
 inline int make_tmap_16b(CUtensorMap* out, int dtype, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box, TmapSwizzle swz = TM_SWZ_128) {
   auto fn = tmap_encode_fn();
@@ -102,7 +102,7 @@ inline int make_tmap_16b(CUtensorMap* out, int dtype, const void* base, int rank
   CUresult r = fn(out, dtype == PA_DTYPE_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                        : dtype == PA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                   (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swz == TM_SWZ_128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  swz == TM_SWZ_128 ? CU_TENSOR_MAP_SWIZZLE_128B : swz == TM_SWZ_64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
                                      (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);

@@ -374,6 +374,22 @@ __global__ void copy16_kernel(const uint4* __restrict__ src, uint4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp32 -> fp16 / bf16 cast of an activation tensor (opt-in fp32-input mode of the drop-ins: the reference's forward takes
+// fp32 tensors, ViT.py:79): 32 bytes in, 16 bytes out per thread step, grid sized in multiples of the SM count
+__global__ void cast_f32_to_16_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long long n8, int to_bf16,
+                                      const float* __restrict__ tail_src, uint16_t* __restrict__ tail_dst, int tail) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(src + 2 * i), b = __ldg(src + 2 * i + 1);
+    dst[i] = to_bf16 ? make_uint4(pack_bf2(a.x, a.y), pack_bf2(a.z, a.w), pack_bf2(b.x, b.y), pack_bf2(b.z, b.w))
+                     : make_uint4(pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(b.x, b.y), pack_h2(b.z, b.w));
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail) {
+    const float v = tail_src[threadIdx.x];
+    tail_dst[threadIdx.x] = to_bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // LePE (cswin.py:86-99): depthwise 3x3 over each cross-shaped window of V, zero padded AT WINDOW BORDERS,
 // written (fp16) into the attention output buffer at the image position of the token; the attention epilogue
 // then adds its softmax(QK^T)V on top.  v: column slice [v_col0, v_col0+Cb) of the [B, L, ldv] qkv buffer.

@@ -10,7 +10,7 @@ from torch import nn
 
 from . import _lib as L
 from . import ops
-from ._common import ParamStage, check_forward_mode, f32, w16
+from ._common import StagedModule, check_forward_mode, f32, w16
 
 
 def _get_v_t(conv):
@@ -18,7 +18,7 @@ def _get_v_t(conv):
     return conv.weight.detach().float().reshape(C, 9).t().contiguous()     # [9, C]
 
 
-class LePEAttention(nn.Module):
+class LePEAttention(StagedModule):
     """Cross-shaped-window attention with locally-enhanced positional encoding.  ``forward(qkv[3,B,L,C])``: the
     three slices may be strided views (the block passes channel halves of one buffer, cswin.py:188-189).
     Launches: LePE depthwise-3x3 kernel, then the windowed tcgen05 attention core that gathers windows by TMA and
@@ -48,7 +48,7 @@ class LePEAttention(nn.Module):
         self.W_sp = W_sp
         self.get_v = nn.Conv2d(dim, dim, kernel_size=3, stride=1, padding=1, groups=dim)
         self.attn_drop = nn.Dropout(attn_drop)
-        self._stage = ParamStage()
+        self._init_stage()
 
     def staged_get_v(self):
         return self._stage.get("v", (self.get_v.weight, self.get_v.bias), lambda: (_get_v_t(self.get_v), f32(self.get_v.bias)))
@@ -95,7 +95,7 @@ class Mlp(nn.Module):
         return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
 
 
-class CSWinBlock(nn.Module):
+class CSWinBlock(StagedModule):
     """Same constructor and ``state_dict`` keys as the reference block (cswin.py:132-174).  ``attention_half(x)``
     is the B200 path (norm1 -> qkv -> two LePE branches -> proj -> residual, cswin.py:181-194) as ONE C-ABI call;
     ``forward`` adds the MLP half with ordinary PyTorch modules (cswin.py:195)."""
@@ -131,9 +131,10 @@ class CSWinBlock(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=mlp_hidden_dim, out_features=dim, act_layer=act_layer, drop=drop)
         self.norm2 = norm_layer(dim)
         self.out_dtype = None
-        self._stage = ParamStage()
+        self._init_stage()
 
     def attention_half(self, x, residual=True):
+        x, y_dtype = self._prepare_input(x)
         check_forward_mode(self, x, (self.proj_drop.p, self.attns[0].attn_drop.p))
         if not isinstance(self.norm1, nn.LayerNorm):
             raise NotImplementedError("only norm_layer=nn.LayerNorm is implemented on the B200 path")
@@ -145,7 +146,7 @@ class CSWinBlock(nn.Module):
             "w", (q.weight, q.bias, p.weight, p.bias, n1.weight, n1.bias),
             lambda: (w16(q.weight, torch.float16), f32(q.bias), w16(p.weight, torch.float16), f32(p.bias),
                      f32(n1.weight), f32(n1.bias)))
-        y = torch.empty(B, Lt, C, dtype=self.out_dtype or x.dtype, device=x.device)
+        y = torch.empty(B, Lt, C, dtype=self.out_dtype or y_dtype, device=x.device)
         a = L.CswinBlockArgs()
         a.dtype, a.out_dtype = ops.dtype_code(x.dtype), ops.dtype_code(y.dtype)
         a.B, a.L, a.C, a.H = B, Lt, C, self.num_heads
@@ -163,7 +164,10 @@ class CSWinBlock(nn.Module):
         return y
 
     def forward(self, x):
-        x = self.attention_half(x, residual=True)
-        with torch.no_grad():
-            x = x + self.mlp(self.norm2(x))
-        return x
+        """cswin.py:176-197.  The attention half is the B200 path; the MLP half (cswin.py:195, outside the hot path) runs the
+        block's own PyTorch modules in THEIR parameter dtype, so the block works in a 16-bit model as well as in an fp32 model
+        whose attention half is fed 16-bit activations (or fp32 ones with ``fp32_input`` set); the result has x's dtype."""
+        y = self.attention_half(x, residual=True)
+        y = y.to(self.norm2.weight.dtype)
+        y = y + self.mlp(self.norm2(y))
+        return y.to(x.dtype)

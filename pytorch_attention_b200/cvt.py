@@ -6,11 +6,11 @@ from torch import nn
 
 from . import _lib as L
 from . import ops
-from ._common import ParamStage, check_forward_mode, f32, w16
+from ._common import StagedModule, check_forward_mode, f32, w16
 from .pvt import fold_bn
 
 
-class Attention(nn.Module):
+class Attention(StagedModule):
     """NCHW in / NCHW out, same constructor and ``state_dict`` keys as the reference (cvt.py:49-62).
     Launch sequence: depthwise-conv+BN (NCHW -> token-major) -> qkv GEMM -> attention core -> proj GEMM that
     writes NCHW directly (y[b] = Wp . O[b]^T, bias per row)."""
@@ -30,7 +30,7 @@ class Attention(nn.Module):
         self.proj = nn.Conv2d(dim, dim, 1)
         self.proj_drop = nn.Dropout(proj_drop)
         self.out_dtype = None
-        self._stage = ParamStage()
+        self._init_stage()
 
     def _staged(self):
         dw, bn, pw = self.conv_proj_qkv[0], self.conv_proj_qkv[1], self.conv_proj_qkv[2]
@@ -46,13 +46,14 @@ class Attention(nn.Module):
         return self._stage.get("w", srcs, build)
 
     def forward(self, x):
+        x, y_dtype = self._prepare_input(x)
         check_forward_mode(self, x, (self.attn_drop.p, self.proj_drop.p))
         if self.training:
             raise NotImplementedError("train-mode BatchNorm (batch statistics) is not implemented: call .eval()")
         B, C, H, W = x.shape
         x = x.contiguous()
         s = self._staged()
-        y = torch.empty(B, C, H, W, dtype=self.out_dtype or x.dtype, device=x.device)
+        y = torch.empty(B, C, H, W, dtype=self.out_dtype or y_dtype, device=x.device)
         a = L.CvtArgs()
         a.dtype, a.out_dtype = ops.dtype_code(x.dtype), ops.dtype_code(y.dtype)
         a.B, a.C, a.H, a.Himg, a.Wimg, a.ks = B, C, self.num_heads, H, W, self.ks

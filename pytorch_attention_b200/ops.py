@@ -47,6 +47,17 @@ def workspace(nbytes, device):
     return buf
 
 
+def cast_f32(x, dtype):
+    """fp32 CUDA tensor -> contiguous fp16 / bf16 copy, by this library's cast kernel (pa_cast_f32)."""
+    require_cuda(x)
+    assert x.dtype == torch.float32 and dtype in (torch.float16, torch.bfloat16)
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.load().pa_cast_f32(_ptr(x), _ptr(out), x.numel(), dtype_code(dtype), stream_ptr(x.device)))
+    return out
+
+
 def gemm_tn(a, b, bias=None, out=None, out_dtype=None, bias_mode=None, block_n=0, residual=None, cluster=0):
     """out[z][m,n] = sum_k a[z][m,k] b[z][n,k] (+bias).  a: [M,K] or [Z,M,K]; b: [N,K] or [Z,N,K] (row pitch may
     exceed K); bias fp32 per column (default) or per row (bias_mode=2)."""

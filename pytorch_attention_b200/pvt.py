@@ -6,7 +6,7 @@ from torch import nn
 
 from . import _lib as L
 from . import ops
-from ._common import ParamStage, check_forward_mode, f32, w16
+from ._common import StagedModule, check_forward_mode, f32, w16
 
 
 def fold_bn(conv_bias, bn: nn.BatchNorm2d):
@@ -23,7 +23,7 @@ def _cat_bias(*bs):
     return torch.cat([b.detach().float() for b in bs]).contiguous()
 
 
-class Attention(nn.Module):
+class Attention(StagedModule):
     """Same constructor / ``forward(x[B,N,C], H, W)`` / ``state_dict`` keys as the reference (pvt.py:53-71):
     ``q,k,v,proj`` Linear and, for sr_ratio > 1, ``sr = Sequential(Conv2d(depthwise, k=s=sr), BatchNorm2d)``.
     Launch sequence: [sr conv+BN kernel] -> q GEMM -> fused [k|v] GEMM -> attention core -> proj GEMM."""
@@ -46,7 +46,7 @@ class Attention(nn.Module):
                 nn.Conv2d(dim, dim, kernel_size=sr_ratio, stride=sr_ratio, groups=dim),
                 nn.BatchNorm2d(dim))
         self.out_dtype = None
-        self._stage = ParamStage()
+        self._init_stage()
 
     def _staged(self, dtype):
         srcs = [self.q.weight, self.q.bias, self.k.weight, self.k.bias, self.v.weight, self.v.bias,
@@ -69,13 +69,14 @@ class Attention(nn.Module):
         return self._stage.get(("w", dtype), srcs, build)
 
     def forward(self, x, H, W):
+        x, y_dtype = self._prepare_input(x)
         check_forward_mode(self, x, (self.attn_drop.p, self.proj_drop.p))
         if self.sr_ratio > 1 and self.training:
             raise NotImplementedError("train-mode BatchNorm (batch statistics) is not implemented: call .eval()")
         B, N, C = x.shape
         x = x.contiguous()
         s = self._staged(x.dtype)
-        y = torch.empty(B, N, C, dtype=self.out_dtype or x.dtype, device=x.device)
+        y = torch.empty(B, N, C, dtype=self.out_dtype or y_dtype, device=x.device)
         a = L.PvtArgs()
         a.dtype, a.out_dtype = ops.dtype_code(x.dtype), ops.dtype_code(y.dtype)
         a.B, a.N, a.C, a.H = B, N, C, self.num_heads

@@ -9,15 +9,16 @@ from torch import nn
 
 from . import _lib as L
 from . import ops
-from ._common import ParamStage, check_forward_mode, f32, w16
+from ._common import StagedModule, check_forward_mode, f32, w16
 
 
-class Attention(nn.Module):
+class Attention(StagedModule):
     """Same constructor, ``forward(x[B,N,C]) -> [B,N,C]`` contract and ``state_dict`` keys
     (``qkv.weight``, [``qkv.bias``], ``proj.weight``, ``proj.bias``) as the reference class (ViT.py:68-77).
 
-    forward = three stream-ordered launches from libpa_b200.so:
-    tcgen05 GEMM (qkv) -> tcgen05/TMEM softmax-attention core -> tcgen05 GEMM (proj)."""
+    forward = ONE launch from libpa_b200.so for 64-wide heads and N <= 240 (the co-scheduled kernel: qkv / proj tcgen05 GEMMs
+    running under the tcgen05/TMEM softmax chain), otherwise the sequenced single-launch kernel or three stream-ordered
+    launches (other head dims: multiples of 16 up to 192, e.g. the reference's default num_heads=4 at dim 768)."""
 
     def __init__(self, dim, num_heads=4, qkv_bias=False, attn_drop=0, proj_drop=0):
         super().__init__()
@@ -30,7 +31,7 @@ class Attention(nn.Module):
         self.proj = nn.Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
         self.out_dtype = None          # None: same dtype as x.  torch.float16/float32 selectable (bf16 y cannot meet 1e-3)
-        self._stage = ParamStage()
+        self._init_stage()
 
     def _staged(self, dtype):
         q, p = self.qkv, self.proj
@@ -39,11 +40,12 @@ class Attention(nn.Module):
             lambda: (w16(q.weight, dtype), f32(q.bias), w16(p.weight, torch.float16), f32(p.bias)))
 
     def forward(self, x):
+        x, y_dtype = self._prepare_input(x)
         check_forward_mode(self, x, (self.attn_drop.p, self.proj_drop.p))
         B, N, C = x.shape
         x = x.contiguous()
         wq, bq, wp, bp = self._staged(x.dtype)
-        y = torch.empty(B, N, C, dtype=self.out_dtype or x.dtype, device=x.device)
+        y = torch.empty(B, N, C, dtype=self.out_dtype or y_dtype, device=x.device)
         a = L.VitArgs()
         a.dtype, a.out_dtype = ops.dtype_code(x.dtype), ops.dtype_code(y.dtype)
         a.B, a.N, a.C, a.H = B, N, C, self.num_heads

@@ -6,10 +6,10 @@ from torch import nn
 
 from . import _lib as L
 from . import ops
-from ._common import ParamStage, check_forward_mode, f32, w16
+from ._common import StagedModule, check_forward_mode, f32, w16
 
 
-class _XcitBase(nn.Module):
+class _XcitBase(StagedModule):
     def _common_init(self, dim, num_heads, qkv_bias, attn_drop, proj_drop):
         self.num_heads = num_heads
         self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
@@ -17,7 +17,7 @@ class _XcitBase(nn.Module):
         self.proj = nn.Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
         self.out_dtype = None
-        self._stage = ParamStage()
+        self._init_stage()
 
     def _args(self, x, y, extra_srcs=()):
         q, p = self.qkv, self.proj
@@ -43,9 +43,10 @@ class XCA(_XcitBase):
         self._common_init(dim, num_heads, qkv_bias, attn_drop, proj_drop)
 
     def forward(self, x):
+        x, y_dtype = self._prepare_input(x)
         check_forward_mode(self, x, (self.attn_drop.p, self.proj_drop.p))
         x = x.contiguous()
-        y = torch.empty(x.shape, dtype=self.out_dtype or x.dtype, device=x.device)
+        y = torch.empty(x.shape, dtype=self.out_dtype or y_dtype, device=x.device)
         a = self._args(x, y)
         temp = self._stage.get("t", (self.temperature,), lambda: self.temperature.detach().float().reshape(-1).contiguous())
         a.temperature = ops._ptr(temp)
@@ -63,10 +64,16 @@ class ClassAttention(_XcitBase):
         self._common_init(dim, num_heads, qkv_bias, attn_drop, proj_drop)
 
     def forward(self, x):
+        x_in = x
+        x, y_dtype = self._prepare_input(x)
         check_forward_mode(self, x, (self.attn_drop.p, self.proj_drop.p))
         x = x.contiguous()
         y = torch.empty_like(x)
         a = self._args(x, y)
         a.scale = float(self.scale)
         ops.run_with_workspace(x, a, "pa_class_attn_workspace_bytes", "pa_class_attn_fwd")
+        if y_dtype != y.dtype:
+            # fp32_input mode: the CLS row comes from the 16-bit path, the patch tokens pass through UNCHANGED (xcit.py:187)
+            y = y.to(y_dtype)
+            y[:, 1:] = x_in[:, 1:]
         return y

@@ -37,7 +37,7 @@ def rel_max(y, ref):
 def build_dropin(spec, params, out_dtype=None):
     """Instantiate the B200 drop-in for a golden/oracle case spec and load the reference state_dict into it."""
     import pytorch_attention_b200 as pa
-    cls = {"vit": pa.vit.Attention, "pvt": pa.pvt.Attention, "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention,
+    cls = {"vit": pa.vit.Attention, "setr": pa.setr.Attention, "moat": pa.moat.Attention, "pvt": pa.pvt.Attention, "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention,
            "cswin_block": pa.cswin.CSWinBlock, "xca": pa.xcit.XCA, "class_attn": pa.xcit.ClassAttention}[spec["variant"]]
     m = cls(**spec["ctor"]).eval()
     m.load_state_dict(params)          # strict: keys and shapes must match the reference's

@@ -39,7 +39,7 @@ def test_vit_argument_validation_without_gpu():
     a.B, a.N, a.C, a.H = 2, 197, 768, 5          # 768 % 5 != 0  (ViT.py:70 assert)
     assert lib.pa_vit_fwd(C.byref(a), None, 0, None) == L.PA_ERR_BAD_SHAPE
     assert b"divisible" in lib.pa_last_error()
-    a.H = 16                                      # head_dim 48: not a multiple of 32
+    a.H = 32                                      # head_dim 24: not a multiple of 16
     assert lib.pa_vit_fwd(C.byref(a), None, 0, None) == L.PA_ERR_UNSUPPORTED
     a.H = 4                                       # head_dim 192 (the reference's default, ViT.py:67) is served
     assert lib.pa_vit_workspace_bytes(C.byref(a)) > 0
@@ -60,8 +60,8 @@ def test_gemm_and_attn_argument_validation_without_gpu():
     at.q = at.kv = at.o = 16
     at.G, at.H, at.n_q, at.n_k, at.scale = 1, 1, 8, 300, -1.0
     assert lib.pa_attn_core(C.byref(at), None) == L.PA_ERR_UNSUPPORTED  # scale must be > 0
-    at.scale, at.head_dim = 1.0, 48
-    assert lib.pa_attn_core(C.byref(at), None) == L.PA_ERR_UNSUPPORTED  # head_dim 48
+    at.scale, at.head_dim = 1.0, 40
+    assert lib.pa_attn_core(C.byref(at), None) == L.PA_ERR_UNSUPPORTED  # head_dim 40: not a multiple of 16
 
 
 def test_variant_argument_validation_without_gpu():

@@ -36,7 +36,7 @@ def _oracle_case(spec, seed=0, dtype=torch.float16):
 
 def _init_sd(spec):
     import pytorch_attention_b200 as pa
-    cls = {"vit": pa.vit.Attention, "pvt": pa.pvt.Attention, "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention,
+    cls = {"vit": pa.vit.Attention, "setr": pa.setr.Attention, "moat": pa.moat.Attention, "pvt": pa.pvt.Attention, "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention,
            "cswin_block": pa.cswin.CSWinBlock, "xca": pa.xcit.XCA, "class_attn": pa.xcit.ClassAttention}[spec["variant"]]
     return cls(**spec["ctor"]).state_dict()
 
@@ -128,3 +128,20 @@ def test_train_mode_batchnorm_is_an_explicit_error():
     m.train()
     with pytest.raises(NotImplementedError):
         m(x, 14, 14)
+
+
+def test_cswin_block_full_forward_in_an_fp32_model_and_a_16bit_model():
+    """CSWinBlock.forward = B200 attention half + the block's own PyTorch MLP half (cswin.py:176-197), against the oracle's
+    attention half followed by the same MLP in fp32: works in a .half() model and, with fp32_input set, in an fp32 model."""
+    spec = dict(variant="cswin_block", ctor=dict(dim=128, reso=14, num_heads=4, split_size=7, qkv_bias=True), x=(2, 196, 128))
+    m, x, ref_half = _oracle_case(spec, seed=5)
+    with torch.no_grad():
+        mc = m.float().cpu()
+        ref = ref_half + mc.mlp(mc.norm2(ref_half))
+        m = m.cuda()
+        m.fp32_input = torch.float16
+        y32 = m(x.float())                                 # fp32 model, fp32 activations
+        assert y32.dtype == torch.float32
+        y16 = m.half()(x)                                  # 16-bit model
+        assert y16.dtype == torch.float16
+    assert rel_fro(y32.cpu(), ref) < 2e-3 and rel_fro(y16.float().cpu(), ref) < 3e-3

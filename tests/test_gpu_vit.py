@@ -210,6 +210,9 @@ def test_vit_co_scheduled_kernel_inside_cuda_graph_and_second_stream():
                                      (512, 4, 2, 197),      # head_dim 128
                                      (384, 4, 2, 130),      # head_dim 96 (three 32-wide panels)
                                      (640, 4, 2, 64),       # head_dim 160, a single key block
+                                     (192, 4, 2, 197),      # head_dim 48 (three 16-wide panels): moat_0's heads, moat.py:144-146
+                                     (320, 4, 2, 100),      # head_dim 80
+                                     (352, 2, 1, 70),       # head_dim 176
                                      (256, 8, 2, 197),      # head_dim 32 through the ViT entry point
                                      (384, 2, 1, 600)])     # head_dim 192, ten key blocks
 def test_vit_other_head_dims_vs_oracle(C, H, B, N):
@@ -242,3 +245,35 @@ def test_vit_reference_default_constructor_runs():
         sd = {k: v.float().cpu() for k, v in m.state_dict().items()}
         ref = vit_attention(x[:2].float().cpu(), sd["qkv.weight"], None, sd["proj.weight"], sd["proj.bias"], 4)
     assert rel_fro(y[:2].float().cpu(), ref) < TOL
+
+
+def test_module_on_the_wrong_device_is_a_clean_error():
+    """Raw parameter pointers go into TMA descriptors: a module left on the CPU must raise, not fault inside a kernel."""
+    import pytorch_attention_b200 as pa
+    m = pa.ViTAttention(128, 2).eval().half()            # parameters stay on the CPU
+    with pytest.raises(RuntimeError, match="move the module"):
+        m(torch.randn(1, 8, 128, device="cuda").half())
+
+
+def test_fp32_input_is_opt_in_and_matches_the_16bit_path():
+    """The reference's forward is fp32 in / fp32 out (ViT.py:79).  Default: fp32 x is an explicit error; with
+    ``fp32_input = torch.float16`` x is cast by this library's kernel (pa_cast_f32) and y comes back in fp32."""
+    m, x = _fresh(256, 4, 3, 197, 17)
+    m = m.cuda()                                          # fp32 parameters, as in a stock fp32 model
+    xg = x.float().cuda()
+    with torch.no_grad():
+        with pytest.raises(ValueError, match="fp32_input"):
+            m(xg)
+        m.fp32_input = torch.float16
+        y = m(xg)
+        assert y.dtype == torch.float32
+        m.fp32_input = None
+        m.out_dtype = torch.float32
+        assert torch.equal(y, m(xg.half()))               # x holds fp16-representable values: the cast is exact
+    sd = {k: v.float().cpu() for k, v in m.state_dict().items()}
+    ref = vit_attention(x.float(), sd["qkv.weight"], None, sd["proj.weight"], sd["proj.bias"], 4)
+    assert rel_fro(y.cpu(), ref) < TOL
+    # odd element counts exercise the cast kernel's tail
+    from pytorch_attention_b200 import ops
+    t = torch.randn(1003, device="cuda")
+    assert torch.equal(ops.cast_f32(t, torch.bfloat16), t.bfloat16()) and torch.equal(ops.cast_f32(t, torch.float16), t.half())

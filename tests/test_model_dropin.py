@@ -85,11 +85,12 @@ def _swap_targets():
         "cvt": ("cvt_13", {"Attention": pa.cvt.Attention}),
         "cswin": ("CSWin_64_12211_tiny_224", {"LePEAttention": pa.cswin.LePEAttention, "CSWinBlock": pa.cswin.CSWinBlock}),
         "xcit": ("xcit_nano_12_p16", {"XCA": pa.xcit.XCA, "ClassAttention": pa.xcit.ClassAttention}),
+        "moat": ("moat_0", {"Attention": pa.moat.Attention}),      # 48- and 96-wide heads (dims 384 / 768, 8 heads)
     }
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted")
-@pytest.mark.parametrize("modname", ["pvt", "cvt", "cswin", "xcit"])
+@pytest.mark.parametrize("modname", ["pvt", "cvt", "cswin", "xcit", "moat"])
 def test_class_swap_in_the_reference_zoo_models(modname, monkeypatch):
     """The reference's own model constructors build the drop-ins with the reference's arguments, and a stock model's
     state_dict loads strictly into the swapped model (same keys, same shapes) -- for every model family on the path."""

@@ -44,7 +44,7 @@ def test_unsupported_modes_raise():
     from pytorch_attention_b200._common import check_forward_mode
 
     class Fake:  # a CUDA-looking tensor stand-in is not constructible here; exercise the dtype / mode checks
-        is_cuda, dtype, requires_grad = True, torch.float32, False
+        is_cuda, dtype, requires_grad, device = True, torch.float32, False, torch.device("cpu")
     m = pa.ViTAttention(128, 2, attn_drop=0.1)
     with pytest.raises(ValueError):
         check_forward_mode(m.eval(), Fake(), (0.1,))
@@ -52,6 +52,9 @@ def test_unsupported_modes_raise():
     with pytest.raises(NotImplementedError):
         check_forward_mode(m.train(), Fake(), (0.1,))
     check_forward_mode(m.eval(), Fake(), (0.1,))
+    Fake.device = torch.device("cuda", 0)          # parameters elsewhere than the input: a clean error, not a bad pointer in a kernel
+    with pytest.raises(RuntimeError, match="move the module"):
+        check_forward_mode(m.eval(), Fake(), (0.1,))
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
@@ -62,3 +65,71 @@ def test_vit_matches_live_reference_contract():
     m = pa.ViTAttention(192, 3, qkv_bias=True)
     assert {k: v.shape for k, v in r.state_dict().items()} == {k: v.shape for k, v in m.state_dict().items()}
     m.load_state_dict(r.state_dict())          # reference weights load unchanged
+
+
+def test_setr_moat_defaults_and_keys():
+    """setr.Attention / moat.Attention: ViT's parameters with the constructor default num_heads=8 (setr.py:51, moat.py:63)."""
+    for cls in (pa.setr.Attention, pa.moat.Attention):
+        m = cls(256)
+        assert m.num_heads == 8 and m.scale == 32 ** -0.5
+        assert sorted(m.state_dict()) == ["proj.bias", "proj.weight", "qkv.weight"]
+        with pytest.raises(AssertionError):       # setr.py:53 / moat.py:65
+            cls(100, 3)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
+@pytest.mark.parametrize("modname", ["setr", "moat"])
+def test_setr_moat_match_live_reference_contract(modname):
+    from oracle.cases import load_reference_class
+    ref = load_reference_class(REF, modname, "Attention")
+    ours = getattr(pa, modname).Attention
+    assert str(inspect.signature(ref.__init__)) == str(inspect.signature(ours.__init__))
+    r = ref(256, qkv_bias=True)
+    m = ours(256, qkv_bias=True)
+    assert {k: v.shape for k, v in r.state_dict().items()} == {k: v.shape for k, v in m.state_dict().items()}
+    m.load_state_dict(r.state_dict())
+
+
+def test_param_stage_is_dropped_when_parameters_may_have_changed():
+    """load_state_dict and every _apply (.to / .half / .float ...) clear the staged 16-bit copies; refresh() does it on demand
+    (in-place edits through .data do not bump a tensor's version counter)."""
+    m = pa.ViTAttention(128, 2).eval()
+    m._stage.get("k", (m.qkv.weight,), lambda: "staged")
+    assert m._stage._entries
+    m.load_state_dict(m.state_dict())
+    assert not m._stage._entries
+    m._stage.get("k", (m.qkv.weight,), lambda: "staged")
+    m.half()
+    assert not m._stage._entries
+    m._stage.get("k", (m.qkv.weight,), lambda: "staged")
+    m.refresh()
+    assert not m._stage._entries
+    blk = pa.CSWinBlock(64, 14, 2)
+    blk.attns[0]._stage.get("k", (), lambda: 1)
+    blk.refresh()
+    assert not blk.attns[0]._stage._entries
+
+
+def test_build_is_atomic_and_locked(tmp_path, monkeypatch):
+    """build_lib compiles to a temporary name and renames it into place under a file lock; a second caller that finds the
+    library fresh after taking the lock does not compile again."""
+    from pytorch_attention_b200 import build as b
+    calls = []
+
+    def fake_run(cmd, capture_output, text):
+        out = cmd[cmd.index("-o") + 1]
+        assert out != b.LIB_PATH and out.startswith(b.LIB_PATH + ".tmp.")
+        open(out, "wb").write(b"x")
+        calls.append(out)
+
+        class R:
+            returncode, stdout, stderr = 0, "", ""
+        return R()
+    monkeypatch.setattr(b, "LIB_DIR", str(tmp_path))
+    monkeypatch.setattr(b, "LIB_PATH", str(tmp_path / "libpa_b200.so"))
+    monkeypatch.setattr(b.subprocess, "run", fake_run)
+    b.build_lib(force=True)
+    assert len(calls) == 1 and (tmp_path / "libpa_b200.so").read_bytes() == b"x"
+    assert not list(tmp_path.glob("*.tmp.*"))
+    b.build_lib()                       # fresh: no second compile
+    assert len(calls) == 1
