@@ -6,6 +6,7 @@
 #include "pa_cosched.cuh"
 #include "pa_host.cuh"
 #include "pa_misc.cuh"
+#include "pa_xca.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -1000,12 +1001,32 @@ int pa_xca_fwd(const pa_xcit_args* a, void* workspace, size_t workspace_bytes, v
   void* qkv = ws.take((size_t)rows * 3 * C * 2);
   void* ob = ws.take((size_t)rows * C * 2);
   if ((rc = linear(a->x, a->dtype, C, a->qkv_weight, a->dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
-  XcaParams xp;
-  xp.qkv = qkv; xp.out = ob; xp.temperature = a->temperature; xp.B = a->B; xp.N = a->N; xp.C = C; xp.H = a->H;
-  if (C / a->H == 64) xca_core_kernel<64><<<a->B * a->H, 256, 0, st>>>(xp);
-  else xca_core_kernel<32><<<a->B * a->H, 256, 0, st>>>(xp);
-  PA_CUDA_OK(cudaGetLastError());
-  launch_counter()++;
+  // cross-covariance core on the tensor cores (pa_xca.cuh): one unit per (image, 128-channel group)
+  {
+    CUtensorMap tm;
+    uint64_t dims[3] = {(uint64_t)(3 * C), (uint64_t)a->N, (uint64_t)a->B};
+    uint64_t str[2] = {(uint64_t)(3 * C) * 2, (uint64_t)a->N * 3 * C * 2};
+    uint32_t box[3] = {64, 128, 1};
+    if ((rc = make_tmap_16b(&tm, PA_DTYPE_F16, qkv, 3, dims, str, box, TM_SWZ_128))) return rc;
+    XcaTcParams xp = {};
+    xp.B = a->B; xp.N = a->N; xp.C = C; xp.H = a->H;
+    xp.groups = (C + 127) / 128; xp.units = a->B * xp.groups; xp.nchunks = (a->N + 127) / 128;
+    xp.temperature = a->temperature; xp.out = ob;
+    xp.idesc_mn = make_idesc(128, 128, PA_F16, PA_F16, 1, 1);
+    xp.idesc_k = make_idesc(128, 128, PA_F16, PA_F16, 0, 0);
+    const int grid = xp.units < num_sms() ? xp.units : num_sms();
+    if (C / a->H == 64) {
+      static SmemAttr smem_attr;
+      if ((rc = smem_attr.ensure(xca_tc_kernel<64>, XT_SMEM))) return rc;
+      xca_tc_kernel<64><<<grid, XT_THREADS, XT_SMEM, st>>>(tm, xp);
+    } else {
+      static SmemAttr smem_attr;
+      if ((rc = smem_attr.ensure(xca_tc_kernel<32>, XT_SMEM))) return rc;
+      xca_tc_kernel<32><<<grid, XT_THREADS, XT_SMEM, st>>>(tm, xp);
+    }
+    PA_CUDA_OK(cudaGetLastError());
+    launch_counter()++;
+  }
   return linear(ob, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st);
 }
 

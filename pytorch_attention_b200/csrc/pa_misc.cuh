@@ -212,98 +212,6 @@ __global__ void layernorm_kernel(const LnParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// XCA core (xcit.py:251-262) for one (batch, head): q,k,v are [N, 64] fp16 column slices of the qkv buffer.
-//   A[d,e] = softmax_e( temperature * <q[:,d], k[:,e]> / (max(|q[:,d]|,eps) max(|k[:,e]|,eps)) ),   O[n,d] = sum_e A[d,e] v[n,e]
-// 256 threads: thread (ty,tx) owns the 4x4 block A[4ty..][4tx..]; tokens streamed through smem in chunks.
-// L2 norms reduce over the token axis: per-thread partials + warp-shuffle/smem reduction.
-struct XcaParams {
-  const void* qkv; void* out; const float* temperature;
-  int B, N, C, H;
-};
-constexpr int XCA_CHUNK = 32;
-template <int HD>                       // head dim 64, or 32 (the zoo's xcit_nano: dim 128, 4 heads)
-__global__ void __launch_bounds__(256) xca_core_kernel(const XcaParams p) {
-  constexpr int BLK = HD / 16;          // each of the 16 x 16 threads owns a BLK x BLK block of A
-  constexpr int TPR = 256 / HD;         // threads per softmax row
-  __shared__ float sq[XCA_CHUNK][HD + 1], sk[XCA_CHUNK][HD + 1];
-  __shared__ float A[HD][HD + 1];
-  __shared__ float qn[HD], kn[HD];
-  const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const long long ld = 3LL * p.C;
-  const __half* base = reinterpret_cast<const __half*>(p.qkv) + (long long)b * p.N * ld + h * HD;
-  float acc[BLK][BLK] = {};
-  float nq = 0.f, nk = 0.f;         // thread tid<HD: sum of squares of column tid of q; HD<=tid<2HD: of k
-  for (int n0 = 0; n0 < p.N; n0 += XCA_CHUNK) {
-    for (int i = tid; i < XCA_CHUNK * HD; i += 256) {
-      const int r = i / HD, c = i % HD;
-      const bool ok = (n0 + r) < p.N;
-      sq[r][c] = ok ? __half2float(base[(long long)(n0 + r) * ld + c]) : 0.f;
-      sk[r][c] = ok ? __half2float(base[(long long)(n0 + r) * ld + p.C + c]) : 0.f;
-    }
-    __syncthreads();
-    if (tid < HD) {
-      for (int r = 0; r < XCA_CHUNK; ++r) nq = fmaf(sq[r][tid], sq[r][tid], nq);
-    } else if (tid < 2 * HD) {
-      for (int r = 0; r < XCA_CHUNK; ++r) nk = fmaf(sk[r][tid - HD], sk[r][tid - HD], nk);
-    }
-    for (int r = 0; r < XCA_CHUNK; ++r) {
-      float a[BLK], bb[BLK];
-#pragma unroll
-      for (int i = 0; i < BLK; ++i) { a[i] = sq[r][BLK * ty + i]; bb[i] = sk[r][BLK * tx + i]; }
-#pragma unroll
-      for (int i = 0; i < BLK; ++i)
-#pragma unroll
-        for (int j = 0; j < BLK; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-  if (tid < HD) qn[tid] = fmaxf(sqrtf(nq), 1e-12f);            // F.normalize eps (xcit.py:255)
-  else if (tid < 2 * HD) kn[tid - HD] = fmaxf(sqrtf(nk), 1e-12f);
-  __syncthreads();
-  const float temp = __ldg(p.temperature + h);
-#pragma unroll
-  for (int i = 0; i < BLK; ++i)
-#pragma unroll
-    for (int j = 0; j < BLK; ++j) A[BLK * ty + i][BLK * tx + j] = acc[i][j] / (qn[BLK * ty + i] * kn[BLK * tx + j]) * temp;
-  __syncthreads();
-  // row softmax over e: TPR threads per row, shuffle reductions
-  {
-    const int row = tid / TPR, part = tid % TPR;
-    float mx = -INFINITY;
-    for (int e = part; e < HD; e += TPR) mx = fmaxf(mx, A[row][e]);
-#pragma unroll
-    for (int o = 1; o < TPR; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-    for (int e = part; e < HD; e += TPR) { const float ex = __expf(A[row][e] - mx); A[row][e] = ex; sum += ex; }
-#pragma unroll
-    for (int o = 1; o < TPR; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.f / sum;
-    for (int e = part; e < HD; e += TPR) A[row][e] *= inv;
-  }
-  __syncthreads();
-  // O[n, d] = sum_e A[d][e] v[n][e]; v streamed through sq
-  __half* outb = reinterpret_cast<__half*>(p.out) + (long long)b * p.N * p.C + h * HD;
-  for (int n0 = 0; n0 < p.N; n0 += XCA_CHUNK) {
-    for (int i = tid; i < XCA_CHUNK * HD; i += 256) {
-      const int r = i / HD, c = i % HD;
-      sq[r][c] = (n0 + r) < p.N ? __half2float(base[(long long)(n0 + r) * ld + 2 * p.C + c]) : 0.f;
-    }
-    __syncthreads();
-    for (int i = tid; i < XCA_CHUNK * HD; i += 256) {
-      const int r = i / HD, d = i % HD;
-      if (n0 + r < p.N) {
-        float o = 0.f;
-#pragma unroll 16
-        for (int e = 0; e < HD; ++e) o = fmaf(A[d][e], sq[r][e], o);
-        outb[(long long)(n0 + r) * p.C + d] = __float2half_rn(o);
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // ClassAttention core (xcit.py:180-185) for one (batch, head): only the CLS (token 0) query attends.
 struct ClsParams {
   const void* qkv; void* out;    // qkv [B, N, 3C] fp16; out [B, C] fp16
