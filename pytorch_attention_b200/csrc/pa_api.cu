@@ -947,8 +947,14 @@ int pa_cvt_fwd(const pa_cvt_args* a, void* workspace, size_t workspace_bytes, vo
   DwParams dp;
   dp.x = a->x; dp.out = tok; dp.w = a->dw_weight; dp.scale = a->dw_scale; dp.shift = a->dw_shift;
   dp.B = a->B; dp.C = C; dp.H = a->Himg; dp.W = a->Wimg; dp.ks = a->ks; dp.dtype = a->dtype;
-  dim3 grid((HW + 31) / 32, (C + 31) / 32, a->B);
-  dwconv_bn_to_tokens_kernel<<<grid, 256, 0, st>>>(dp);
+  const int dw3_smem = 32 * (((DW3_RB + 2) * a->Wimg) | 1) * (int)sizeof(float);
+  if (a->ks == 3 && dw3_smem <= 48 * 1024 && a->B <= 65535) {
+    dim3 grid(a->B, (C + 31) / 32, (a->Himg + DW3_RB - 1) / DW3_RB);
+    dwconv3_bn_to_tokens_kernel<<<grid, 256, dw3_smem, st>>>(dp);
+  } else {
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, a->B);
+    dwconv_bn_to_tokens_kernel<<<grid, 256, 0, st>>>(dp);
+  }
   PA_CUDA_OK(cudaGetLastError());
   launch_counter()++;
   // 1x1 conv == linear over channels   (cvt.py:58), rows ordered (s,h,d) as ViT (cvt.py:66)

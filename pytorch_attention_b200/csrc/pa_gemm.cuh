@@ -295,6 +295,17 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
       const int mt = tw.mg * CLUSTER + crank;
       const int row = mt * GEMM_BLOCK_M + trow;
       const int col0 = tw.col0;
+      const bool row_ok = row < p.M;
+      // 16-bit residual rows with 16-byte aligned pitch: prefetched one sub-tile ahead (issued before the wait for the accumulator)
+      const bool res_fast = !LEAN && p.residual != nullptr && p.res_dtype != 2 && (p.ldr % 8) == 0 && (p.r_batch % 8) == 0 &&
+                            (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0;
+      uint4 rpre[4];
+      if (!LEAN && res_fast && row_ok && eset < active_sets && col0 + eset * 32 + 32 <= p.N) {
+        const uint4* rp4 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + (long long)z * p.r_batch +
+                                                          (long long)row * p.ldr + col0 + eset * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rpre[i] = __ldg(rp4 + i);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (p.signal_ctr != nullptr && leader && pending_mt >= 0) {
@@ -303,7 +314,6 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
       pending_mt = mt;
       if (tracer) trace_stamp(p, tseq, 4);
       const uint32_t t_base = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      const bool row_ok = row < p.M;
       const float bias_m = (!LEAN && p.bias_mode == 2 && row_ok) ? p.bias[row] : 0.f;
       const long long d_off = (long long)z * p.d_batch + (long long)row * p.ldd;
       float* sbias = reinterpret_cast<float*>(smem + Cfg::BIAS_OFFSET);
@@ -338,35 +348,39 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
         }
         if (!LEAN && p.residual != nullptr && row_ok) {
           const long long r_off = (long long)z * p.r_batch + (long long)row * p.ldr + col;
-          if (p.res_dtype == 2) {
+          if (res_fast && col + 32 <= p.N) {
+            // this row's 32 residual values were requested one sub-tile ago (rpre): with 227 KB of shared memory there is no
+            // L1 left, so each 16-byte load is an L2 round trip -- in line they cost a biased + residual GEMM half its rate
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t w[4] = {rpre[i].x, rpre[i].y, rpre[i].z, rpre[i].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (p.res_dtype == 0) {
+                  const __half2 h = *reinterpret_cast<const __half2*>(&w[k]);
+                  f[8 * i + 2 * k] += __low2float(h); f[8 * i + 2 * k + 1] += __high2float(h);
+                } else {
+                  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+                  f[8 * i + 2 * k] += __low2float(h); f[8 * i + 2 * k + 1] += __high2float(h);
+                }
+              }
+            }
+            const int ncol = col + 32 * active_sets;
+            if (c + 32 * active_sets < tw.ncols && ncol + 32 <= p.N) {
+              const uint4* rp4 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + r_off + 32 * active_sets);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) rpre[i] = __ldg(rp4 + i);
+            }
+          } else if (p.res_dtype == 2) {
             const float* rp = reinterpret_cast<const float*>(p.residual) + r_off;
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __ldg(rp + i) : 0.f;
+          } else if (p.res_dtype == 0) {
+            const __half* hp = reinterpret_cast<const __half*>(p.residual) + r_off;
+            for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __half2float(__ldg(hp + i)) : 0.f;
           } else {
-            const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + r_off;
-            if (col + 32 <= p.N && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {               // 4 x 16-byte loads of this row's 32 residual values
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (p.res_dtype == 0) {
-                    const __half2 h = *reinterpret_cast<const __half2*>(&w[k]);
-                    f[8 * i + 2 * k] += __low2float(h); f[8 * i + 2 * k + 1] += __high2float(h);
-                  } else {
-                    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-                    f[8 * i + 2 * k] += __low2float(h); f[8 * i + 2 * k + 1] += __high2float(h);
-                  }
-                }
-              }
-            } else if (p.res_dtype == 0) {
-              const __half* hp = reinterpret_cast<const __half*>(rp);
-              for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __half2float(__ldg(hp + i)) : 0.f;
-            } else {
-              const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(rp);
-              for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __bfloat162float(__ldg(bp + i)) : 0.f;
-            }
+            const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_off;
+            for (int i = 0; i < 32; ++i) f[i] += (col + i < p.N) ? __bfloat162float(__ldg(bp + i)) : 0.f;
           }
         }
         if (LEAN || p.tma_store) {

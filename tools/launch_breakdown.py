@@ -16,3 +16,5 @@ go(pa.cswin.CSWinBlock(512, 56, 16, split_size=7, qkv_bias=True), torch.randn(12
 go(pa.xcit.XCA(768, 12), torch.randn(64, 196, 768, device=dev).half(), lambda m, x: m(x))
 go(pa.cvt.Attention(384, 6), torch.randn(64, 384, 14, 14, device=dev).half(), lambda m, x: m(x))
 go(pa.xcit.ClassAttention(768, 12), torch.randn(64, 197, 768, device=dev).half(), lambda m, x: m(x))
+go(pa.cswin.CSWinBlock(512, 7, 16, split_size=7, qkv_bias=True, last_stage=True), torch.randn(128, 49, 512, device=dev).half(), lambda m, x: m.attention_half(x))
+go(pa.vit.Attention(768, 4), torch.randn(64, 197, 768, device=dev).half(), lambda m, x: m(x))
