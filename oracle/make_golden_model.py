@@ -65,5 +65,38 @@ def main():
     print("wrote", os.path.join(out, "vit_tiny.npz"))
 
 
+DEFAULT_SEED = 77
+
+
+def main_default():
+    """tests/golden/models/vit_default.npz: the reference's ``VisionTransformer()`` with EVERY constructor default (224x224,
+    patch 16, 12 blocks, dim 768, 4 heads of 192, 1000 classes -- README.md:331-334) on two images.  Parameters come from
+    oracle.model_glue.synth_state_dict (seeded), so only the logits are stored."""
+    sys.path.insert(0, REF)
+    import ViT
+    from oracle import vit_attention
+    from oracle.model_glue import vit_model_forward, attention_state, vit_state_shapes, synth_state_dict
+    model = ViT.VisionTransformer().eval()
+    shapes = vit_state_shapes()
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == shapes, "restated shapes differ from the live model"
+    sd = synth_state_dict(shapes, DEFAULT_SEED)
+    model.load_state_dict(sd, strict=True)
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(DEFAULT_SEED)).half().float()
+    with torch.no_grad():
+        logits = model(x)
+
+        def oracle_attn(i, t):
+            a = attention_state(sd, i)
+            return vit_attention(t, a["qkv.weight"], a.get("qkv.bias"), a["proj.weight"], a["proj.bias"], 4)
+        glue = vit_model_forward(sd, x, oracle_attn, 16, 12)
+    err = (glue - logits).abs().max().item()
+    print(f"default VisionTransformer(): logits{tuple(logits.shape)} max|y|={logits.abs().max():.4f}  glue+oracle vs reference max-abs = {err:.3e}")
+    assert err <= 5e-5 * max(1.0, logits.abs().max().item())
+    out = os.path.join(ROOT, "tests", "golden", "models", "vit_default.npz")
+    np.savez_compressed(out, y_ref=logits.numpy().astype(np.float32), seed=np.int64(DEFAULT_SEED))
+    print("wrote", out)
+
+
 if __name__ == "__main__":
     main()
+    main_default()

@@ -40,3 +40,55 @@ def attention_state(sd, i):
     """The sub-state_dict of blocks[i].attn with the keys the Attention module itself uses."""
     p = f"blocks.{i}.attn."
     return {k[len(p):]: v for k, v in sd.items() if k.startswith(p)}
+
+
+def vit_state_shapes(image_size=224, patch_size=16, in_channels=3, depths=12, num_heads=4, mlp_ratio=4, embedding_dim=768,
+                     qkv_bias=False, num_classes=1000, **_unused):
+    """Keys and shapes of the reference ``ViT.VisionTransformer(...)`` state_dict for a configuration (defaults = the
+    reference's own defaults, ViT.py:121-134).  oracle/make_golden_model.py asserts it against the live model."""
+    D, P = embedding_dim, patch_size
+    n = (image_size // patch_size) ** 2
+    hid = int(D * mlp_ratio)
+    sh = {"cls_token": (1, 1, D), "position_embedding": (1, n + 1, D),
+          "patch_embedding.proj.weight": (D, in_channels, P, P), "patch_embedding.proj.bias": (D,)}
+    for i in range(depths):
+        p = f"blocks.{i}."
+        sh[p + "attn.qkv.weight"] = (3 * D, D)
+        if qkv_bias:
+            sh[p + "attn.qkv.bias"] = (3 * D,)
+        sh[p + "attn.proj.weight"] = (D, D)
+        sh[p + "attn.proj.bias"] = (D,)
+        for ln in ("layernorm1", "layernorm2"):
+            sh[p + ln + ".weight"] = (D,)
+            sh[p + ln + ".bias"] = (D,)
+        sh[p + "mlp.fc1.weight"] = (hid, D)
+        sh[p + "mlp.fc1.bias"] = (hid,)
+        sh[p + "mlp.fc2.weight"] = (D, hid)
+        sh[p + "mlp.fc2.bias"] = (D,)
+    sh["head.weight"] = (num_classes, D)
+    sh["head.bias"] = (num_classes,)
+    return sh
+
+
+def synth_state_dict(shapes, seed):
+    """Deterministic parameters from a seed (one CPU generator per tensor, in sorted key order), rounded once to
+    fp16-representable values: lets a whole-model golden be stored as logits only (an 86 M-parameter ViT-B would not fit a
+    fixture) -- generator and test rebuild the identical state_dict."""
+    sd = {}
+    for idx, key in enumerate(sorted(shapes)):
+        g = torch.Generator().manual_seed(seed * 100003 + idx)
+        shape = shapes[key]
+        t = torch.randn(shape, generator=g)
+        if key.endswith("layernorm1.weight") or key.endswith("layernorm2.weight"):
+            t = 1.0 + 0.1 * t
+        elif key in ("cls_token", "position_embedding"):
+            t = 0.1 * t
+        elif len(shape) >= 2:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            t = t * (1.0 / fan_in ** 0.5)
+        else:
+            t = 0.05 * t
+        sd[key] = t.half().float()
+    return sd

@@ -526,6 +526,23 @@ static int launch_vit_fused(const GemmPlan& p1, const AttnPlan& pa_, const GemmP
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  {
+    // the phases spin-wait on each other across SMs: launch only a grid the device can hold at once (one CTA per SM; for
+    // this one-CTA-per-SM kernel the occupancy calculator's answer is exact), else let the caller use three launches
+    static std::mutex mu;
+    static int resident[64];
+    static int resident_smem[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    std::lock_guard<std::mutex> lk(mu);
+    if (resident_smem[dev] != smem) {
+      int n = 0;
+      PA_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, vit_fused_kernel<BN1, BN2>, &cfg));
+      resident[dev] = n; resident_smem[dev] = smem;
+    }
+    if (resident[dev] < (int)cfg.gridDim.x / 2) return 1;
+  }
   PA_CUDA_OK(cudaLaunchKernelEx(&cfg, vit_fused_kernel<BN1, BN2>, p1.tmA, p1.tmB, p1.tmD, pa_.tq, pa_.tk, pa_.tv, pa_.to, p2.tmA, p2.tmB,
                                 p2.tmD, fp));
   return PA_OK;
@@ -797,10 +814,13 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
       else if (bn1 == 256) rc = launch_vit_fused<256, 256>(p1, pa_, p2, fp, smem, st);
       else if (bn2 == 256) rc = launch_vit_fused<192, 256>(p1, pa_, p2, fp, smem, st);
       else rc = launch_vit_fused<192, 192>(p1, pa_, p2, fp, smem, st);
-      if (rc) return rc;
-      launch_counter()++;
-      t_last_vit_path = 2;
-      return PA_OK;
+      if (rc < 0) return rc;
+      if (rc == 0) {
+        launch_counter()++;
+        t_last_vit_path = 2;
+        return PA_OK;
+      }
+      if (fused_forced) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(fused): the device cannot hold one CTA of the kernel on every SM at once");
     }
   }
   t_last_vit_path = 1;

@@ -145,3 +145,57 @@ def test_cswin_block_full_forward_in_an_fp32_model_and_a_16bit_model():
         y16 = m.half()(x)                                  # 16-bit model
         assert y16.dtype == torch.float16
     assert rel_fro(y32.cpu(), ref) < 2e-3 and rel_fro(y16.float().cpu(), ref) < 3e-3
+
+
+# ---------------------------------------------------------------- BASELINE configurations at FULL batch: size-independent properties
+def _full_batch_properties(m, x, call, k):
+    """Images are independent in eval mode: (1) a batch permutation permutes the output bit-exactly -- at full
+    batch this exercises the persistent schedulers' wrap-around and every tile position; (2) the first k images of the full
+    batch equal, bit for bit, the same k images run alone -- and THAT small run is what the oracle tests above pin."""
+    with torch.no_grad():
+        y = call(m, x)
+        perm = torch.randperm(x.shape[0], device=x.device)
+        assert torch.equal(call(m, x[perm]), y[perm])
+        assert torch.equal(call(m, x[:k].contiguous()), y[:k])
+    return y
+
+
+def test_c3_pvt_full_batch_properties_and_oracle_slice():
+    """BASELINE.json configs[2]: PvT SR-Attention sr_ratio=8, B=32, H=W=64, dim=512."""
+    spec = ORACLE_CASES["pvt_c3_b2"]
+    m, x2, ref2 = _oracle_case(spec, seed=9)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(32, 4096, 512, device="cuda", generator=g).half()
+    x[:2] = x2
+    y = _full_batch_properties(m, x, lambda mod, t: mod(t, 64, 64), 2)
+    assert rel_fro(y[:2].float().cpu(), ref2) < TOL
+
+
+def test_c4_cswin_full_batch_properties_and_oracle_slice():
+    """BASELINE.json configs[3]: CSWin cross-window attention, 224x224 (reso 56), B=128, dim=512, split=7: 16 384 windows per
+    branch."""
+    spec = ORACLE_CASES["cswin_c4_b1"]
+    m, x1, ref1 = _oracle_case(spec, seed=4)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(128, 3136, 512, device="cuda", generator=g).half()
+    x[:1] = x1
+    y = _full_batch_properties(m, x, lambda mod, t: mod.attention_half(t), 1)
+    assert rel_fro(y[:1].float().cpu(), ref1) < TOL
+
+
+def test_c5_vit_l_shard_all_images_vs_oracle():
+    """BASELINE.json configs[4] per-GPU shard: ViT-L/16 attention, 64 images, dim 1024, 16 heads -- EVERY image against the oracle."""
+    import pytorch_attention_b200 as pa
+    from oracle import vit_attention
+    torch.manual_seed(12)
+    m = pa.ViTAttention(1024, 16).eval()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(p.half().float())
+    x = torch.randn(64, 197, 1024).half()
+    sd = {k: v.float() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = vit_attention(x.float(), sd["qkv.weight"], None, sd["proj.weight"], sd["proj.bias"], 16)
+        y = m.cuda()(x.cuda()).float().cpu()
+    per_image = ((y - ref).flatten(1).norm(dim=1) / ref.flatten(1).norm(dim=1))
+    assert per_image.max().item() < TOL, per_image.max().item()

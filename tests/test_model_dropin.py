@@ -108,3 +108,60 @@ def test_class_swap_in_the_reference_zoo_models(modname, monkeypatch):
     n_stock = sum(type(m).__name__ in swaps for m in stock.modules())
     assert n_dropins == n_stock and n_dropins > 0
     swapped.load_state_dict(sd, strict=True)
+
+
+# ---------------------------------------------------------------- the reference's DEFAULT model: VisionTransformer()
+def _load_default():
+    from oracle.model_glue import vit_state_shapes, synth_state_dict
+    z = np.load(os.path.join(GOLDEN_DIR, "models", "vit_default.npz"))
+    seed = int(z["seed"])
+    sd = synth_state_dict(vit_state_shapes(), seed)              # 86 M parameters rebuilt from the seed (only logits are stored)
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(seed)).half().float()
+    return sd, x, torch.from_numpy(z["y_ref"])
+
+
+def test_default_model_glue_with_oracle_attention_reproduces_reference_logits():
+    """`VisionTransformer()` with every constructor default (12 blocks, dim 768, 4 heads of 192: README.md:331-334)."""
+    sd, x, y_ref = _load_default()
+
+    def attn(i, t):
+        a = attention_state(sd, i)
+        return vit_attention(t, a["qkv.weight"], a.get("qkv.bias"), a["proj.weight"], a["proj.bias"], 4)
+
+    with torch.no_grad():
+        y = vit_model_forward(sd, x, attn, 16, 12)
+    assert (y - y_ref).abs().max().item() <= 5e-5 * y_ref.abs().max().item()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted")
+def test_default_reference_model_accepts_the_dropin_and_the_synthetic_state(monkeypatch):
+    import pytorch_attention_b200 as pa
+    from oracle.model_glue import vit_state_shapes, synth_state_dict
+    monkeypatch.syspath_prepend(REF)
+    import ViT
+    monkeypatch.setattr(ViT, "Attention", pa.vit.Attention)
+    model = ViT.VisionTransformer()                                # every default: 4 heads of 192
+    assert all(b.attn.num_heads == 4 for b in model.blocks)
+    model.load_state_dict(synth_state_dict(vit_state_shapes(), 77), strict=True)
+
+
+@pytest.mark.gpu
+def test_default_model_with_dropin_attention_matches_reference_logits():
+    """The INTEGRATION.md §1 example at full size: the reference's default ViT (192-wide heads -> the panelled attention
+    core) with the B200 drop-in in all 12 blocks, against the logits of the real reference model."""
+    import pytorch_attention_b200 as pa
+    sd, x, y_ref = _load_default()
+    dev = torch.device("cuda", 0)
+    sdg = {k: v.to(dev) for k, v in sd.items()}
+    mods = []
+    for i in range(12):
+        m = pa.vit.Attention(768).eval()                            # constructor defaults, as ViT.py:111 builds it
+        m.load_state_dict(attention_state(sd, i), strict=True)
+        m = m.to(dev)
+        m.fp32_input = torch.float16                                # fp32 model: opt-in cast, fp32 result
+        mods.append(m)
+    with torch.no_grad():
+        y = vit_model_forward(sdg, x.to(dev), lambda i, t: mods[i](t), 16, 12).cpu()
+    # 12 blocks of a 1e-3 path with fp16-rounded attention inputs, amplified by the MLPs and the head
+    assert rel_fro(y, y_ref) < 1e-2, rel_fro(y, y_ref)
+    assert (y.argmax(-1) == y_ref.argmax(-1)).all()
