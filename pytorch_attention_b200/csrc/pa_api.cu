@@ -39,7 +39,7 @@ struct EnvCfg {
   int vit_fused = -1;        // -1 unset, 0 three launches, 1 single launch required
   int vit_cosched = -1;      // -1 unset (co-scheduled kernel when it qualifies), 0 never, 1 required
   int fused_bn1 = 0, fused_bn2 = 0;
-  int cs_debug = 0;
+  int cs_debug = 0, cs_lag = 0;
 };
 std::atomic<const EnvCfg*> g_env{nullptr};
 std::mutex g_env_mu;
@@ -63,6 +63,7 @@ const EnvCfg* env_load() {
   c->fused_bn1 = env_int("PA_FUSED_BN1", 0);
   c->fused_bn2 = env_int("PA_FUSED_BN2", 0);
   c->cs_debug = env_int("PA_CS_DEBUG", 0);
+  c->cs_lag = env_int("PA_CS_LAG", 0);
   return c;
 }
 inline const EnvCfg& env() {
@@ -752,6 +753,15 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
           g.bias = gp[i]->p.bias; g.out_dtype = gp[i]->p.out_dtype; g.idesc = gp[i]->p.idesc;
         }
         cp.K = C;
+        {
+          // tile order of the GEMM stream: all qkv tiles first, then the proj tiles (lag = m_groups).  Interleaving the proj
+          // tiles of early images (PA_CS_LAG = how many m-groups they trail their rows' qkv tiles) was measured and is WORSE:
+          // ViT-B 86 us at lag 50 (= all first), 95 at 18, 123 at 9, 199 at 1 -- the attention stream runs behind the qkv
+          // production, a proj tile that waits for it stalls its worker's later qkv tiles, and that starves the attention further
+          const int MG = cp.g[0].m_groups;
+          int lag = ev.cs_lag > 0 ? ev.cs_lag : MG;
+          cp.lag = lag < 1 ? 1 : lag > MG ? MG : lag;
+        }
         cp.d[0] = qkv; cp.d[1] = a->y;
         cp.at = pa_.p;
         cp.g[0].signal_ctr = counters;                       // per 128-row tile of qkv: every epilogue warp of every column tile

@@ -73,6 +73,7 @@ struct CsParams {
   CsGemmPhase g[2];        // qkv projection, output projection (both contract over K)
   void* d[2];              // their outputs, row-major [M, N] 16-bit (contiguous rows)
   int K;
+  int lag;                 // tile order: the proj tiles of m-group j follow the qkv tiles of m-group j + lag (see cs_tile)
   AttnParams at;
   int* sched;
   long long* trace;        // debug: per CTA {role, worker, start, first unit ready, end} on the global timer, or nullptr
@@ -99,6 +100,32 @@ __device__ __forceinline__ long long cs_globaltimer() {
 __device__ __forceinline__ void cs_regs_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 48;" ::: "memory"); }
 __device__ __forceinline__ void cs_regs_worker() { asm volatile("setmaxnreg.inc.sync.aligned.u32 96;" ::: "memory"); }
 
+// Global tile order of role G.  All qkv tiles of an m-group come before that m-group's proj tiles, `lag` m-groups later:
+//     qkv(0) .. qkv(lag-1) | qkv(lag) proj(0) | qkv(lag+1) proj(1) | ... | qkv(MG-1) proj(MG-1-lag) | proj(MG-lag) .. proj(MG-1)
+// lag = m_groups (the default) is "all qkv tiles, then all proj tiles".  Smaller lags were built to take the proj tiles of the
+// last images off the kernel's tail and measured (tools/cosched_lag_sweep.py): they are slower, the smaller the worse -- the
+// attention stream trails the qkv production, so an interleaved proj tile usually waits and holds up the qkv tiles queued
+// behind it in its worker.  The order is deadlock-free for any lag >= 1: a proj tile waits
+// for attention units that need only qkv tiles of m-groups <= its own + 1, all EARLIER in this order, and qkv tiles wait for
+// nothing -- by induction over the order every tile's dependencies complete.
+struct CsTile { int ph, mg, nt; };
+__device__ __forceinline__ CsTile cs_tile(const CsParams& P, int t) {
+  const int n1 = P.g[0].n_tiles, n2 = P.g[1].n_tiles, MG = P.g[0].m_groups, D = P.lag;
+  CsTile r;
+  if (t < D * n1) { r.ph = 0; r.mg = t / n1; r.nt = t - r.mg * n1; return r; }
+  t -= D * n1;
+  const int per = n1 + n2, s = t / per;
+  if (s < MG - D) {
+    const int q = t - s * per;
+    if (q < n1) { r.ph = 0; r.mg = D + s; r.nt = q; }
+    else { r.ph = 1; r.mg = s; r.nt = q - n1; }
+    return r;
+  }
+  t -= (MG - D) * per;
+  r.ph = 1; r.mg = MG - D + t / n2; r.nt = t % n2;
+  return r;
+}
+
 // ================================================================================================ role G
 __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUtensorMap& tmB1, const CUtensorMap& tmD1,
                                              const CUtensorMap& tmA2, const CUtensorMap& tmB2, const CUtensorMap& tmD2,
@@ -120,10 +147,9 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
     int stage = 0, tseq = 0;
     uint32_t phase = 0;
     for (int t = worker; t < T; t += nworkers, ++tseq) {
-      const int ph = t >= T0;
+      const CsTile tl = cs_tile(P, t);
+      const int ph = tl.ph, mg = tl.mg, nt = tl.nt;
       const CsGemmPhase& g = P.g[ph];
-      const int r = ph ? t - T0 : t;
-      const int mg = r / g.n_tiles, nt = r - mg * g.n_tiles;
       const int mt = mg * 2 + crank;
       const CUtensorMap* tA = ph ? &tmA2 : &tmA1;
       const CUtensorMap* tB = ph ? &tmB2 : &tmB1;
@@ -155,7 +181,7 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
       uint32_t phase = 0, acc_phase = 0;
       const uint32_t smem_base = smem_u32(smem);
       for (int t = worker; t < T; t += nworkers, ++tseq) {
-        const uint32_t idesc = P.g[t >= T0].idesc;
+        const uint32_t idesc = P.g[cs_tile(P, t).ph].idesc;
         mbar_wait(tempty_bar, acc_phase ^ 1);           // single accumulator: drained by both CTAs' epilogue warps
         acc_phase ^= 1;
         tc_fence_after();
@@ -191,10 +217,9 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
     int tseq = 0;
     const bool tracer = (warp == 4 && lane == 0);
     for (int t = worker; t < T; t += nworkers, ++tseq) {
-      const int ph = t >= T0;
+      const CsTile tl = cs_tile(P, t);
+      const int ph = tl.ph, mg = tl.mg, nt = tl.nt;
       const CsGemmPhase& g = P.g[ph];
-      const int r = ph ? t - T0 : t;
-      const int mg = r / g.n_tiles, nt = r - mg * g.n_tiles;
       const int mt = mg * 2 + crank;
       const int row0 = mt * GEMM_BLOCK_M + q * 32;
       const CUtensorMap* tD = ph ? &tmD2 : &tmD1;
