@@ -496,6 +496,8 @@ __device__ __forceinline__ void cs_attn_role(const CUtensorMap& tmQ, const CUten
         float s0 = 0.f, s1 = 0.f;
         // (measured again in this kernel, two softmax warps per scheduler instead of four: with the TMEM load of step k+1 in
         //  flight during step k the pass takes 3.3 k cycles instead of 2.45 k alone, 4.2 k instead of 2.9 k next to the GEMM role)
+        // (also measured: 32 columns per TMEM round trip -- 2.45 k vs 2.34 k cycles, no gain: the pass is bound by the MUFU /
+        //  issue rate of the two softmax warps per scheduler, not by the number of round trips)
 #pragma unroll 1
         for (int k = 0; k < nst; ++k) {
           tmem_ld16(t_my + k * 16, va);
