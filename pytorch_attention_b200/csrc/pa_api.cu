@@ -39,7 +39,7 @@ struct EnvCfg {
   int vit_fused = -1;        // -1 unset, 0 three launches, 1 single launch required
   int vit_cosched = -1;      // -1 unset (co-scheduled kernel when it qualifies), 0 never, 1 required
   int fused_bn1 = 0, fused_bn2 = 0;
-  int cs_debug = 0, cs_lag = 0;
+  int cs_debug = 0, cs_lag = 0, gemm_one_set = 0;
 };
 std::atomic<const EnvCfg*> g_env{nullptr};
 std::mutex g_env_mu;
@@ -64,6 +64,7 @@ const EnvCfg* env_load() {
   c->fused_bn2 = env_int("PA_FUSED_BN2", 0);
   c->cs_debug = env_int("PA_CS_DEBUG", 0);
   c->cs_lag = env_int("PA_CS_LAG", 0);
+  c->gemm_one_set = getenv("PA_GEMM_ONE_SET") != nullptr;
   return c;
 }
 inline const EnvCfg& env() {
@@ -94,11 +95,11 @@ struct SmemAttr {
 };
 
 // ------------------------------------------------------------------------------------------------ GEMM
-template <int BN, int ST, int CL, bool PAIR = false>
+template <int BN, int ST, int CL, bool PAIR = false, int ESETS = 1>
 int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, GemmParams p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, ST, PAIR>;
   static SmemAttr smem_attr;
-  { const int rc = smem_attr.ensure(gemm_tn_kernel<BN, ST, CL, PAIR>, Cfg::SMEM_BYTES); if (rc) return rc; }
+  { const int rc = smem_attr.ensure(gemm_tn_kernel<BN, ST, CL, PAIR, ESETS>, Cfg::SMEM_BYTES); if (rc) return rc; }
   p.m_groups = (p.m_tiles + CL - 1) / CL;
   if (!(PAIR && BN == 256)) p.balanced = 0;
   const int supertiles = p.m_groups * p.n_tiles * p.Z;
@@ -109,7 +110,7 @@ int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
   const int nclusters = supertiles < max_clusters ? supertiles : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * CL);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(128 + 128 * ESETS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -119,7 +120,7 @@ int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
-  PA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, ST, CL, PAIR>, tmA, tmB, tmD, p));
+  PA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, ST, CL, PAIR, ESETS>, tmA, tmB, tmD, p));
   launch_counter()++;
   return PA_OK;
 }
@@ -127,7 +128,12 @@ int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
 template <int BN, int ST>
 int launch_gemm_cl(int cl, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const GemmParams& p,
                    cudaStream_t st) {
-  if (cl == -2) return launch_gemm_cfg<BN, (ST * (128 + BN) * 128) / ((128 + BN / 2) * 128) < 8 ? (ST * (128 + BN)) / (128 + BN / 2) : 8, 2, true>(tmA, tmB, tmD, p, st);
+  if (cl == -2) {
+    constexpr int PST = (ST * (128 + BN) * 128) / ((128 + BN / 2) * 128) < 8 ? (ST * (128 + BN)) / (128 + BN / 2) : 8;
+    // two epilogue warp sets whenever the staged-store path is taken and the tile is wide enough for the drain to matter
+    if (BN >= 128 && p.tma_store && !env().gemm_one_set) return launch_gemm_cfg<BN, PST, 2, true, 2>(tmA, tmB, tmD, p, st);
+    return launch_gemm_cfg<BN, PST, 2, true>(tmA, tmB, tmD, p, st);
+  }
   if (cl == 4) return launch_gemm_cfg<BN, ST, 4>(tmA, tmB, tmD, p, st);
   if (cl == 2) return launch_gemm_cfg<BN, ST, 2>(tmA, tmB, tmD, p, st);
   return launch_gemm_cfg<BN, ST, 1>(tmA, tmB, tmD, p, st);

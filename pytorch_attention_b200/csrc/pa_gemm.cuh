@@ -270,7 +270,8 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
     }
   } else if (warp >= 4 && warp < 4 + 4 * ESETS) {
     // ===================== epilogue (warps 4-7 [+ 8-11]; wider CTAs of the fused kernels leave the rest idle here) ==
-    static_assert(ESETS == 1 || LEAN, "several epilogue sets only on the staged-store path");
+    // several sets exist only on the staged-store path: the fused kernels (LEAN) have no other path, the stand-alone kernel is
+    // launched with ESETS > 1 only when the host established p.tma_store (see launch_gemm_cfg)
     static_assert(ESETS == 1 || ESETS == 2 || ESETS == 4, "1, 2 or 4 epilogue sets");
     const int eset = (warp - 4) >> 2;       // which set of four warps
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -461,8 +462,10 @@ __device__ __forceinline__ void gemm_run(const CUtensorMap& tmA, const CUtensorM
 
 }
 
-template <int BLOCK_N, int STAGES, int CLUSTER, bool PAIR = false>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// ESETS = 2: warps 8-11 join the epilogue (384 threads).  A 256 x 256 x K pair tile's mainloop is K / 64 x 512 cycles; one set of
+// four warps needs ~5 k cycles to drain 256 columns, so for K <= 512 (PVT, CSWin, CvT projections) a single set is the limiter.
+template <int BLOCK_N, int STAGES, int CLUSTER, bool PAIR = false, int ESETS = 1>
+__global__ void __launch_bounds__(128 + 128 * ESETS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, STAGES, PAIR>;
@@ -478,7 +481,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.tma_store) tma_prefetch_desc(&tmD);
   }
   if (warp == 1 && lane == 0) {
-    gemm_init_barriers<STAGES, CLUSTER, PAIR>(bars);
+    gemm_init_barriers<STAGES, CLUSTER, PAIR, ESETS>(bars);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -491,7 +494,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  gemm_run<BLOCK_N, STAGES, CLUSTER, PAIR>(tmA, tmB, tmD, p, smem, bars, tmem_base);
+  gemm_run<BLOCK_N, STAGES, CLUSTER, PAIR, false, ESETS>(tmA, tmB, tmD, p, smem, bars, tmem_base);
 
   tc_fence_before();
   __syncthreads();
