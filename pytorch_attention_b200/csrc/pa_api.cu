@@ -39,7 +39,7 @@ struct EnvCfg {
   int vit_fused = -1;        // -1 unset, 0 three launches, 1 single launch required
   int vit_cosched = -1;      // -1 unset (co-scheduled kernel when it qualifies), 0 never, 1 required
   int fused_bn1 = 0, fused_bn2 = 0;
-  int cs_debug = 0, cs_lag = 0, gemm_one_set = 0;
+  int cs_debug = 0, cs_lag = 0, gemm_one_set = 0, attn_two_slot = 0;
 };
 std::atomic<const EnvCfg*> g_env{nullptr};
 std::mutex g_env_mu;
@@ -65,6 +65,7 @@ const EnvCfg* env_load() {
   c->cs_debug = env_int("PA_CS_DEBUG", 0);
   c->cs_lag = env_int("PA_CS_LAG", 0);
   c->gemm_one_set = getenv("PA_GEMM_ONE_SET") != nullptr;
+  c->attn_two_slot = getenv("PA_ATTN_TWO_SLOT") != nullptr;
   return c;
 }
 inline const EnvCfg& env() {
@@ -448,6 +449,8 @@ int launch_attn_wide(const AttnLaunch& a, cudaStream_t st) {
 inline bool attn_wide_hd(int hd) { return hd % 16 == 0 && hd >= 48 && hd <= 192 && hd != 64; }
 inline bool attn_hd_ok(int hd) { return hd == 32 || hd == 64 || attn_wide_hd(hd); }
 
+int launch_attn_single_slot(const AttnPlan& plan, cudaStream_t st);   // below (needs pa_cosched.cuh's kernel)
+
 int attn_launch(const AttnLaunch& a, cudaStream_t st) {
   if (attn_wide_hd(a.hd)) {
     if (a.windowed) return fail(PA_ERR_UNSUPPORTED, "windowed attention: head_dim %d unsupported (32 or 64)", a.hd);
@@ -472,10 +475,40 @@ int attn_launch(const AttnLaunch& a, cudaStream_t st) {
   int rc = attn_prepare(a, &plan);
   if (rc) return rc;
   const int hd = a.hd;
+  // 64-wide heads, one key block, staged output: two single-slot CTAs per SM (pa_cosched.cuh's attention role as a kernel)
+  if (hd == 64 && !a.windowed && plan.p.nkb == 1 && plan.p.tma_store && plan.p.kb <= 240 && !env().attn_two_slot)
+    return launch_attn_single_slot(plan, st);
   if (hd == 64) return a.windowed ? launch_attn_t<64, true>(plan.tq, plan.tk, plan.tv, plan.to, plan.p, plan.smem, st)
                                   : launch_attn_t<64, false>(plan.tq, plan.tk, plan.tv, plan.to, plan.p, plan.smem, st);
   return a.windowed ? launch_attn_t<32, true>(plan.tq, plan.tk, plan.tv, plan.to, plan.p, plan.smem, st)
                     : launch_attn_t<32, false>(plan.tq, plan.tk, plan.tv, plan.to, plan.p, plan.smem, st);
+}
+
+int launch_attn_single_slot(const AttnPlan& plan, cudaStream_t st) {
+  CsParams cp = {};
+  cp.at = plan.p;
+  cp.at.wait_ctr = nullptr; cp.at.signal_ctr = nullptr;
+  const int smem = cs_attn_bar_offset(plan.p.kb) + 1024;
+  static SmemAttr smem_attr;
+  int rc = smem_attr.ensure(attn_single_slot_kernel, smem);
+  if (rc) return rc;
+  {
+    static std::mutex mu;
+    static bool carve[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (!carve[dev & 63]) {
+      PA_CUDA_OK(cudaFuncSetAttribute(attn_single_slot_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      carve[dev & 63] = true;
+    }
+  }
+  const int units = plan.p.G * plan.p.H * plan.p.q_tiles;
+  const int cap = 2 * num_sms();
+  attn_single_slot_kernel<<<units < cap ? units : cap, CS_THREADS, smem, st>>>(plan.tq, plan.tk, plan.tv, plan.to, cp);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  return PA_OK;
 }
 
 int attn_impl(const pa_attn_args* a, cudaStream_t st) {

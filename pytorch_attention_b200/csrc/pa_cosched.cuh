@@ -668,4 +668,38 @@ vit_cosched_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   }
 }
 
+// The attention role as a kernel of its own (no GEMM role, no dependency counters): two single-slot CTAs per SM instead of the
+// two-slot CTA of attn_core_kernel.  Used for 64-wide heads with a single key block (ViT / PVT / CvT three-launch paths).
+__global__ void __launch_bounds__(CS_THREADS, 2)
+attn_single_slot_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const CsParams P) {
+  extern __shared__ uint8_t cs_raw[];
+  const uint32_t pad = (1024u - (smem_u32(cs_raw) & 1023u)) & 1023u;
+  uint8_t* smem = cs_raw + pad;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pad >= CS_BAR_BYTES ? cs_raw : smem + cs_attn_bar_offset(P.at.kb));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&bars[9], 8);
+    mbar_init(&bars[10], 1);
+    mbar_init(&bars[11], 8);
+    mbar_init(&bars[12], 8);
+    mbar_init(&bars[13], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  cs_attn_role(tmQ, tmK, tmV, tmO, P, smem, bars, tmem_base, (int)blockIdx.x, (int)gridDim.x);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
 }  // namespace pa
