@@ -7,6 +7,7 @@
 #include "pa_host.cuh"
 #include "pa_misc.cuh"
 #include "pa_xca.cuh"
+#include "pa_attn_win.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -39,7 +40,7 @@ struct EnvCfg {
   int vit_fused = -1;        // -1 unset, 0 three launches, 1 single launch required
   int vit_cosched = -1;      // -1 unset (co-scheduled kernel when it qualifies), 0 never, 1 required
   int fused_bn1 = 0, fused_bn2 = 0;
-  int cs_debug = 0, cs_lag = 0, gemm_one_set = 0, attn_two_slot = 0;
+  int cs_debug = 0, cs_lag = 0, gemm_one_set = 0, attn_two_slot = 0, cswin_two_kernels = 0;
 };
 std::atomic<const EnvCfg*> g_env{nullptr};
 std::mutex g_env_mu;
@@ -66,6 +67,7 @@ const EnvCfg* env_load() {
   c->cs_lag = env_int("PA_CS_LAG", 0);
   c->gemm_one_set = getenv("PA_GEMM_ONE_SET") != nullptr;
   c->attn_two_slot = getenv("PA_ATTN_TWO_SLOT") != nullptr;
+  c->cswin_two_kernels = getenv("PA_CSWIN_TWO_KERNELS") != nullptr;
   return c;
 }
 inline const EnvCfg& env() {
@@ -649,6 +651,42 @@ static int launch_vit_cosched(const GemmPlan& p1, const CUtensorMap& tmD1, const
   return PA_OK;
 }
 
+// LePEAttention as ONE kernel (pa_attn_win.cuh: window-resident Q/K/V, LePE in the epilogue).  Returns 1 when the window does not
+// fit the two-CTAs-per-SM shared-memory plan (the caller then runs the LePE kernel + the windowed two-slot core).
+template <int HD>
+static int launch_attn_win(const AttnPlan& plan, const pa_cswin_lepe_args* a, cudaStream_t st) {
+  AttnWinParams wp = {};
+  wp.at = plan.p;
+  wp.at.add_into_out = 0;
+  wp.lepe_w = a->get_v_weight_t; wp.lepe_b = a->get_v_bias; wp.Cb = a->C;
+  wp.q_rows = attn_win_q_rows(plan.p.q_tiles, plan.p.nkb, plan.p.kb_rows);
+  wp.kv_rows = attn_win_kv_rows(plan.p.nkb, plan.p.kb_rows, plan.p.kb);
+  if (plan.p.nkb > 1 && plan.p.kb > 256 - HD) return 1;
+  const int smem = attn_win_data_bytes(HD, wp.q_rows, wp.kv_rows, a->C) + 64 + 1024;
+  if (smem > 115712) return 1;
+  static SmemAttr smem_attr;
+  int rc = smem_attr.ensure(attn_win_kernel<HD>, smem);
+  if (rc) return rc;
+  {
+    static std::mutex mu;
+    static bool carve[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (!carve[dev & 63]) {
+      PA_CUDA_OK(cudaFuncSetAttribute(attn_win_kernel<HD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      carve[dev & 63] = true;
+    }
+  }
+  const int units = plan.p.G * plan.p.H;
+  const int cap = 2 * num_sms();
+  attn_win_kernel<HD><<<units < cap ? units : cap, CS_THREADS, smem, st>>>(plan.tq, plan.tk, plan.tv, wp);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  return PA_OK;
+}
+
+
 extern "C" {
 
 int pa_version(void) { return PA_VERSION; }
@@ -1166,13 +1204,29 @@ static int lepe_run(const pa_cswin_lepe_args* a, cudaStream_t st) {
   if (a->resolution % Hs || a->resolution % Ws) return fail(PA_ERR_BAD_SHAPE, "pa_cswin_lepe: resolution %d not divisible by window %dx%d", a->resolution, Hs, Ws);
   if (a->C % 8 || a->ld % 8 || a->ldo % 8) return fail(PA_ERR_MISALIGNED, "pa_cswin_lepe: channel counts / pitches must be multiples of 8");
   if ((rc = current_device_check())) return rc;
-  // LePE first: out = dwconv3x3(v) per window (cswin.py:93-96) ...
+  if (a->batch_stride != (long long)a->L * a->ld || a->out_batch_stride != (long long)a->L * a->ldo)
+    return fail(PA_ERR_UNSUPPORTED, "pa_cswin_lepe: batch pitch must equal L * row pitch");
+  AttnLaunch at = {};
+  at.hd = a->C / a->H; at.windowed = true; at.H = a->H;
+  at.q = a->q; at.k = a->k; at.v = a->v;
+  at.ldq = a->ld; at.q_group = a->batch_stride; at.ldk = a->ld; at.k_group = a->batch_stride;
+  at.q_col0 = 0; at.k_col0 = 0; at.v_col0 = 0;
+  at.o = a->out; at.ldo = a->ldo; at.o_group = a->out_batch_stride; at.o_col0 = 0;
+  at.scale = a->scale;
+  at.B = a->B; at.R = a->resolution; at.H_sp = Hs; at.W_sp = Ws;
+  // ---- one kernel: windowed attention with the LePE term computed in its epilogue from the resident V (cswin.py:116-125)
+  if (!env().cswin_two_kernels) {
+    AttnPlan plan;
+    at.add_into_out = 0;
+    if ((rc = attn_prepare(at, &plan))) return rc;
+    rc = at.hd == 64 ? launch_attn_win<64>(plan, a, st) : launch_attn_win<32>(plan, a, st);
+    if (rc <= 0) return rc;
+  }
+  // ---- fallback (window too large for the resident plan): LePE first, out = dwconv3x3(v) per window (cswin.py:93-96) ...
   LepeParams lp;
   lp.v = a->v; lp.out = a->out; lp.w = a->get_v_weight_t; lp.bias = a->get_v_bias;
   lp.ldv = a->ld; lp.ldo = a->ldo; lp.v_col0 = 0; lp.o_col0 = 0;
   lp.B = a->B; lp.R = a->resolution; lp.Cb = a->C; lp.H_sp = Hs; lp.W_sp = Ws;
-  if (a->batch_stride != (long long)a->L * a->ld || a->out_batch_stride != (long long)a->L * a->ldo)
-    return fail(PA_ERR_UNSUPPORTED, "pa_cswin_lepe: batch pitch must equal L * row pitch");
   const int lepe_smem = (LEPE_RB + 2) * a->resolution * 128;
   if (a->C % 64 == 0 && lepe_smem <= 48 * 1024) {
     const int nblk = a->B * ((a->resolution + LEPE_RB - 1) / LEPE_RB) * (a->C / 64);
@@ -1183,14 +1237,6 @@ static int lepe_run(const pa_cswin_lepe_args* a, cudaStream_t st) {
   PA_CUDA_OK(cudaGetLastError());
   launch_counter()++;
   // ... then the windowed attention adds softmax(q k^T scale) v on top (cswin.py:116-121) and scatters to image order (122-125)
-  AttnLaunch at = {};
-  at.hd = a->C / a->H; at.windowed = true; at.H = a->H;
-  at.q = a->q; at.k = a->k; at.v = a->v;
-  at.ldq = a->ld; at.q_group = a->batch_stride; at.ldk = a->ld; at.k_group = a->batch_stride;
-  at.q_col0 = 0; at.k_col0 = 0; at.v_col0 = 0;
-  at.o = a->out; at.ldo = a->ldo; at.o_group = a->out_batch_stride; at.o_col0 = 0;
-  at.scale = a->scale;
-  at.B = a->B; at.R = a->resolution; at.H_sp = Hs; at.W_sp = Ws;
   at.add_into_out = 1;
   return attn_launch(at, st);
 }
