@@ -169,8 +169,14 @@ int pick_block_n(int M, int N, int K, int Z, bool pair) {
     const long long waves = (tiles + workers - 1) / workers;
     // MMA cycles per tile (the tensor core walks N in 64-column steps of 32 cycles) + fixed per-tile overhead;
     // narrow tiles pay more shared-memory traffic per flop
-    double per_tile = 2.0 * num_kb * bn + 700.0;
-    if (bn < 128) per_tile *= 1.0 + 0.10 * (128.0 / bn - 1.0);
+    // Pair tiles narrower than 256 columns are bound by the shared-memory port, not by the tensor pipe: per k-block a CTA writes
+    // and reads (128 + bn/2) rows of 128 B against 128 B/clk, the pipe needs 2*bn cycles -> rate cap 2*bn / (128 + bn/2)
+    // (256: 1.0, 192: 0.86, 128: 0.67).  Measured (tools/gemm_trace2.py): 192-wide tiles take 5.0 k cycles per mainloop instead
+    // of 4.6 k, so 450 tiles of 256 beat 600 tiles of 192 on 74 pairs although 6.08 waves round up to 7.
+    double per_tile = 2.0 * num_kb * bn;
+    if (pair) { const double cap = 2.0 * bn / (128.0 + bn / 2.0); if (cap < 1.0) per_tile /= cap; }
+    else if (bn < 128) per_tile *= 1.0 + 0.10 * (128.0 / bn - 1.0);
+    per_tile += 700.0;
     const double cost = waves * per_tile + 0.5 * per_tile;     // + the exposed epilogue of the last tile
     if (cost < best * 0.999) { best = cost; best_bn = bn; }
   }
