@@ -123,6 +123,22 @@ size_t pa_vit_workspace_bytes(const pa_vit_args* a);
 int pa_last_vit_path(void);
 int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------- ViT.TransformerEncoder, attention half  (ViT.py:116) */
+/* y = x + Attention(LayerNorm(x)): the pre-norm and the residual that surround the attention in every ViT-style block
+ * (ViT.py:116, the same shape as pvt.py:106 / setr.py:88 / moat.py).  LayerNorm is this library's row kernel (fp32 statistics,
+ * fp16 output = the qkv GEMM's A operand), the residual is added in the epilogue of the proj GEMM (x is read there once, no
+ * separate elementwise pass, no intermediate attention output in HBM).  Launches: LayerNorm -> GEMM(qkv) -> attention core ->
+ * GEMM(proj + residual). */
+typedef struct {
+  pa_vit_args attn;          /* attn.x = block input (dtype attn.dtype), attn.y = block output of the attention half;
+                                attn.qkv_weight must be fp16 (its input is the fp16 LayerNorm output) */
+  const float* ln_weight;    /* [C] layernorm1.weight */
+  const float* ln_bias;      /* [C] layernorm1.bias */
+  float ln_eps;
+} pa_vit_block_args;
+size_t pa_vit_block_attn_workspace_bytes(const pa_vit_block_args* a);
+int pa_vit_block_attn_fwd(const pa_vit_block_args* a, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- pvt.Attention  (pvt.py:52-91) */
 typedef struct {
   int dtype, out_dtype;

@@ -18,6 +18,7 @@ whenever ``/root/reference`` is mounted.
 """
 from .attention import (  # noqa: F401
     vit_attention,
+    vit_block_attention_half,
     pvt_attention,
     cvt_attention,
     cswin_lepe_attention,

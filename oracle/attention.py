@@ -62,6 +62,15 @@ def vit_attention(x, qkv_weight, qkv_bias, proj_weight, proj_bias, num_heads, sc
     return _lin(o, proj_weight, proj_bias)                      # ViT.py:87
 
 
+def vit_block_attention_half(x, ln_weight, ln_bias, qkv_weight, qkv_bias, proj_weight, proj_bias, num_heads, eps=1e-5):
+    """First half of ViT.TransformerEncoder.forward (ViT.py:116): x + attn(layernorm1(x)).  LayerNorm over the channel axis,
+    biased variance, eps inside the square root (nn.LayerNorm)."""
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    h = (x - mu) / torch.sqrt(var + eps) * ln_weight + ln_bias
+    return x + vit_attention(h, qkv_weight, qkv_bias, proj_weight, proj_bias, num_heads)
+
+
 # --------------------------------------------------------------------------
 # PVT spatial-reduction attention (reference: vision_transformers/pvt.py:52-91)
 # --------------------------------------------------------------------------

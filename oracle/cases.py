@@ -18,6 +18,8 @@ GOLDEN_CASES = {
     "vit_b3_n50_c192_h3_bias": dict(variant="vit", ctor=dict(dim=192, num_heads=3, qkv_bias=True), x=(3, 50, 192)),
     # 192-wide heads (the reference's default ViT.Attention(num_heads=4) at dim 768 has them; here at dim 384 to keep the file small)
     "vit_b2_n197_c384_h2_hd192": dict(variant="vit", ctor=dict(dim=384, num_heads=2), x=(2, 197, 384)),
+    # ViT.TransformerEncoder, attention half: x + attn(layernorm1(x))      ViT.py:105-116
+    "vitblock_b2_n197_c128_h2": dict(variant="vit_block", ctor=dict(dim=128, num_heads=2), x=(2, 197, 128)),
     # setr.Attention(dim, num_heads=8) setr.py:50-72 and moat.Attention(dim, num_heads=8) moat.py:62-84: ViT's math
     "setr_b2_n100_c256_default_heads": dict(variant="setr", ctor=dict(dim=256), x=(2, 100, 256)),
     "moat_b2_n196_c512_default_heads_bias": dict(variant="moat", ctor=dict(dim=512, qkv_bias=True), x=(2, 196, 512)),
@@ -40,6 +42,7 @@ GOLDEN_CASES = {
 
 _REF_CLASS = {
     "vit": ("ViT", "Attention"),
+    "vit_block": ("ViT", "TransformerEncoder"),
     "setr": ("setr", "Attention"),
     "moat": ("moat", "Attention"),
     "pvt": ("pvt", "Attention"),
@@ -121,6 +124,9 @@ def reference_forward(spec, mod, x):
         if v == "cswin_block":
             # attention half only (cswin.py:184-194): x + proj(attn(norm1(x)))
             return cswin_block_attention_half_reference(mod, x)
+        if v == "vit_block":
+            # attention half only (ViT.py:116), with the reference block's own sub-modules
+            return x + mod.attn(mod.layernorm1(x))
         return mod(x)
 
 
@@ -164,6 +170,10 @@ def run_oracle_case(spec, inputs, params, dtype=torch.float32):
         # setr.py:62-72 and moat.py:74-84 restate ViT.py:79-89; their constructor default is 8 heads
         return A.vit_attention(x, P["qkv.weight"], P.get("qkv.bias"), P["proj.weight"], P["proj.bias"],
                                c.get("num_heads", 4 if v == "vit" else 8))
+    if v == "vit_block":
+        return A.vit_block_attention_half(x, P["layernorm1.weight"], P["layernorm1.bias"], P["attn.qkv.weight"],
+                                          P.get("attn.qkv.bias"), P["attn.proj.weight"], P["attn.proj.bias"],
+                                          c.get("num_heads", 4))
     if v == "pvt":
         kw = _kw(P, "q.weight", "q.bias", "k.weight", "k.bias", "v.weight", "v.bias", "proj.weight", "proj.bias",
                  "sr.0.weight", "sr.0.bias", "sr.1.weight", "sr.1.bias", "sr.1.running_mean", "sr.1.running_var")

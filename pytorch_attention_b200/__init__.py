@@ -9,10 +9,11 @@ the reference's file names so that ``from pytorch_attention_b200.pvt import Atte
 from . import _lib, ops  # noqa: F401
 from . import vit, pvt, cvt, cswin, xcit, setr, moat  # noqa: F401
 from .vit import Attention as ViTAttention  # noqa: F401
+from .vit import TransformerEncoder as ViTTransformerEncoder  # noqa: F401
 from .pvt import Attention as PVTAttention  # noqa: F401
 from .cvt import Attention as CvTAttention  # noqa: F401
 from .cswin import LePEAttention, CSWinBlock  # noqa: F401
 from .xcit import XCA, ClassAttention  # noqa: F401
 
-__all__ = ["ops", "vit", "pvt", "cvt", "cswin", "xcit", "setr", "moat", "ViTAttention", "PVTAttention", "CvTAttention",
+__all__ = ["ops", "vit", "pvt", "cvt", "cswin", "xcit", "setr", "moat", "ViTAttention", "ViTTransformerEncoder", "PVTAttention", "CvTAttention",
            "LePEAttention", "CSWinBlock", "XCA", "ClassAttention"]

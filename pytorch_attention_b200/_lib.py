@@ -40,6 +40,10 @@ class VitArgs(C.Structure):
                 ("y", _vp)]
 
 
+class VitBlockArgs(C.Structure):
+    _fields_ = [("attn", VitArgs), ("ln_weight", _vp), ("ln_bias", _vp), ("ln_eps", _f)]
+
+
 class PvtArgs(C.Structure):
     _fields_ = [("dtype", _i), ("out_dtype", _i), ("B", _i), ("N", _i), ("C", _i), ("H", _i),
                 ("Himg", _i), ("Wimg", _i), ("sr", _i), ("scale", _f),
@@ -93,6 +97,8 @@ SYMBOLS = {
     "pa_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitArgs)]),
     "pa_last_vit_path": (_i, []),
     "pa_vit_fwd": (_i, [C.POINTER(VitArgs), _vp, C.c_size_t, _vp]),
+    "pa_vit_block_attn_workspace_bytes": (C.c_size_t, [C.POINTER(VitBlockArgs)]),
+    "pa_vit_block_attn_fwd": (_i, [C.POINTER(VitBlockArgs), _vp, C.c_size_t, _vp]),
     "pa_pvt_workspace_bytes": (C.c_size_t, [C.POINTER(PvtArgs)]),
     "pa_pvt_fwd": (_i, [C.POINTER(PvtArgs), _vp, C.c_size_t, _vp]),
     "pa_cvt_workspace_bytes": (C.c_size_t, [C.POINTER(CvtArgs)]),

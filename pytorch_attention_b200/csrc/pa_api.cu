@@ -743,6 +743,8 @@ static int vit_check(const pa_vit_args* a) {
   return PA_OK;
 }
 
+static int vit_three_launches(const pa_vit_args* a, const void* x_in, int x_dtype, const void* residual, void* qkv, void* obuf, cudaStream_t st);
+
 // dependency counters (per 128-row tile of qkv + per image) followed by the co-scheduled kernel's scheduling words
 static size_t vit_counter_ints(const pa_vit_args* a) {
   const size_t rows = (size_t)a->B * a->N;
@@ -917,10 +919,19 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
     }
   }
   t_last_vit_path = 1;
-  // ---- three launches (any N; also the reference point the fused kernel is tested against)
+  // ---- three launches (any N, any supported head dim; also the reference point the single-launch kernels are tested against)
+  return vit_three_launches(a, a->x, a->dtype, nullptr, qkv, obuf, st);
+}
+
+// qkv GEMM -> attention core -> proj GEMM (+ residual in its epilogue).  x_in: the qkv GEMM's A operand (a->x, or the LayerNorm
+// output of the block entry point); residual: nullptr or the tensor added to proj's result (dtype a->dtype, pitch C).
+static int vit_three_launches(const pa_vit_args* a, const void* x_in, int x_dtype, const void* residual, void* qkv, void* obuf, cudaStream_t st) {
+  int rc;
+  const long long rows = (long long)a->B * a->N;
+  const int C = a->C, hd = C / a->H;
   // 1. qkv[B*N, 3C] = x Wqkv^T (+b)          (ViT.py:81)
-  if ((rc = linear(a->x, a->dtype, C, a->qkv_weight, a->dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
-  // 2. per (b,h): softmax(q k^T scale) v       (ViT.py:83-86), O as [B*N, C] with column h*64+d
+  if ((rc = linear(x_in, x_dtype, C, a->qkv_weight, x_dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
+  // 2. per (b,h): softmax(q k^T scale) v       (ViT.py:83-86), O as [B*N, C] with column h*hd+d
   AttnLaunch at = {};
   at.hd = hd; at.G = a->B; at.H = a->H; at.n_q = a->N; at.n_k = a->N;
   at.q = qkv; at.ldq = 3 * C; at.q_group = (long long)a->N * 3 * C; at.q_col0 = 0;
@@ -928,8 +939,44 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
   at.o = obuf; at.ldo = C; at.o_group = (long long)a->N * C; at.o_col0 = 0;
   at.scale = a->scale;
   if ((rc = attn_launch(at, st))) return rc;
-  // 3. y = O Wproj^T + b                       (ViT.py:87)
-  return linear(obuf, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st);
+  // 3. y = O Wproj^T + b (+ residual)          (ViT.py:87, :116)
+  return linear(obuf, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st,
+                residual, C, a->dtype);
+}
+
+// ================================================================ ViT block, attention half  (ViT.py:116)
+size_t pa_vit_block_attn_workspace_bytes(const pa_vit_block_args* a) {
+  if (!a || vit_check(&a->attn)) return 0;
+  const size_t rows = (size_t)a->attn.B * a->attn.N;
+  return align_up(rows * a->attn.C * 2, 1024) + pa_vit_workspace_bytes(&a->attn);
+}
+
+int pa_vit_block_attn_fwd(const pa_vit_block_args* b, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!b) return fail(PA_ERR_NULL, "pa_vit_block_attn_fwd: args is NULL");
+  const pa_vit_args* a = &b->attn;
+  int rc = vit_check(a);
+  if (rc) return rc;
+  if (!a->x || !a->qkv_weight || !a->proj_weight || !a->y || !b->ln_weight || !b->ln_bias)
+    return fail(PA_ERR_NULL, "pa_vit_block_attn_fwd: x/qkv_weight/proj_weight/y/ln_weight/ln_bias must be non-NULL");
+  if (a->C % 8) return fail(PA_ERR_BAD_SHAPE, "pa_vit_block_attn_fwd: dim must be a multiple of 8");
+  const size_t need = pa_vit_block_attn_workspace_bytes(b);
+  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_vit_block_attn_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+  if ((rc = current_device_check())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long rows = (long long)a->B * a->N;
+  const int C = a->C;
+  Arena ws(workspace);
+  void* img = ws.take((size_t)rows * C * 2);
+  void* qkv = ws.take((size_t)rows * 3 * C * 2);
+  void* obuf = ws.take((size_t)rows * C * 2);
+  // img = layernorm1(x)   (ViT.py:116), fp16
+  LnParams ln;
+  ln.x = a->x; ln.out = img; ln.gamma = b->ln_weight; ln.beta = b->ln_bias; ln.rows = rows; ln.C = C; ln.dtype = a->dtype; ln.eps = b->ln_eps;
+  layernorm_kernel<<<(int)((rows * 32 + 255) / 256), 256, 0, st>>>(ln);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  // x + proj(attention(img)): the residual rides in the proj GEMM's epilogue
+  return vit_three_launches(a, img, PA_DTYPE_F16, a->x, qkv, obuf, st);
 }
 
 /* debug: occupancy facts of the co-scheduled kernel for `smem` bytes of dynamic shared memory; out[0..5] = registers per thread,

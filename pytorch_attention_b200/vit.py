@@ -61,3 +61,68 @@ class Attention(StagedModule):
             L.check(lib.pa_vit_fwd(ctypes.byref(a), ops._ptr(ws), ws.numel(), ops.stream_ptr(x.device)))
         return y
 
+
+
+class Mlp(nn.Module):
+    """ViT.py:47-65 (outside the attention hot path; kept so that TransformerEncoder is a complete drop-in).  The reference applies
+    GELU after fc2 as well."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, drop=0):
+        super().__init__()
+        hidden_features = hidden_features or in_features
+        out_features = out_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.gelu = nn.GELU()
+        self.drop1 = nn.Dropout(drop)
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop2 = nn.Dropout(drop)
+
+    def forward(self, x):
+        return self.drop2(self.gelu(self.fc2(self.drop1(self.gelu(self.fc1(x))))))
+
+
+class TransformerEncoder(StagedModule):
+    """Drop-in for ``ViT.TransformerEncoder`` (ViT.py:105-119): same constructor, sub-module names and ``state_dict`` keys
+    (``attn.*``, ``layernorm1.*``, ``mlp.fc1/fc2.*``, ``layernorm2.*``).
+
+    ``attention_half(x)`` = ``x + attn(layernorm1(x))`` (ViT.py:116) as ONE C-ABI call (``pa_vit_block_attn_fwd``): LayerNorm
+    kernel -> qkv GEMM -> attention core -> proj GEMM with the residual added in its epilogue.  ``forward`` adds the MLP half
+    (ViT.py:117) with the block's own PyTorch modules."""
+
+    def __init__(self, dim, num_heads=4, mlp_ratio=4, qkv_bias=False, attn_drop=0, proj_drop=0):
+        super().__init__()
+        hidden_features = int(dim * mlp_ratio)
+        self.attn = Attention(dim, num_heads, qkv_bias, attn_drop, proj_drop)
+        self.layernorm1 = nn.LayerNorm(dim)
+        self.mlp = Mlp(dim, hidden_features)
+        self.layernorm2 = nn.LayerNorm(dim)
+        self.out_dtype = None
+        self._init_stage()
+
+    def attention_half(self, x):
+        x, y_dtype = self._prepare_input(x)
+        at = self.attn
+        check_forward_mode(self, x, (at.attn_drop.p, at.proj_drop.p))
+        B, N, C = x.shape
+        x = x.contiguous()
+        n1 = self.layernorm1
+        wq, bq, wp, bp, g, b = self._stage.get(
+            "w", (at.qkv.weight, at.qkv.bias, at.proj.weight, at.proj.bias, n1.weight, n1.bias),
+            lambda: (w16(at.qkv.weight, torch.float16), f32(at.qkv.bias), w16(at.proj.weight, torch.float16), f32(at.proj.bias),
+                     f32(n1.weight), f32(n1.bias)))
+        y = torch.empty(B, N, C, dtype=self.out_dtype or y_dtype, device=x.device)
+        a = L.VitBlockArgs()
+        a.attn.dtype, a.attn.out_dtype = ops.dtype_code(x.dtype), ops.dtype_code(y.dtype)
+        a.attn.B, a.attn.N, a.attn.C, a.attn.H = B, N, C, at.num_heads
+        a.attn.scale = float(at.scale)
+        a.attn.x, a.attn.qkv_weight, a.attn.qkv_bias = ops._ptr(x), ops._ptr(wq), ops._ptr(bq)
+        a.attn.proj_weight, a.attn.proj_bias, a.attn.y = ops._ptr(wp), ops._ptr(bp), ops._ptr(y)
+        a.ln_weight, a.ln_bias, a.ln_eps = ops._ptr(g), ops._ptr(b), float(n1.eps)
+        ops.run_with_workspace(x, a, "pa_vit_block_attn_workspace_bytes", "pa_vit_block_attn_fwd")
+        return y
+
+    def forward(self, x):
+        y = self.attention_half(x)
+        y = y.to(self.layernorm2.weight.dtype)
+        y = y + self.mlp(self.layernorm2(y))
+        return y.to(x.dtype)

@@ -37,7 +37,7 @@ def rel_max(y, ref):
 def build_dropin(spec, params, out_dtype=None):
     """Instantiate the B200 drop-in for a golden/oracle case spec and load the reference state_dict into it."""
     import pytorch_attention_b200 as pa
-    cls = {"vit": pa.vit.Attention, "setr": pa.setr.Attention, "moat": pa.moat.Attention, "pvt": pa.pvt.Attention, "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention,
+    cls = {"vit": pa.vit.Attention, "vit_block": pa.vit.TransformerEncoder, "setr": pa.setr.Attention, "moat": pa.moat.Attention, "pvt": pa.pvt.Attention, "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention,
            "cswin_block": pa.cswin.CSWinBlock, "xca": pa.xcit.XCA, "class_attn": pa.xcit.ClassAttention}[spec["variant"]]
     m = cls(**spec["ctor"]).eval()
     m.load_state_dict(params)          # strict: keys and shapes must match the reference's
@@ -51,6 +51,6 @@ def run_dropin(spec, m, x):
     with torch.no_grad():
         if spec["variant"] == "pvt":
             return m(x, *spec["hw"])
-        if spec["variant"] == "cswin_block":
+        if spec["variant"] in ("cswin_block", "vit_block"):
             return m.attention_half(x)
         return m(x)

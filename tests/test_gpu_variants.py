@@ -36,7 +36,7 @@ def _oracle_case(spec, seed=0, dtype=torch.float16):
 
 def _init_sd(spec):
     import pytorch_attention_b200 as pa
-    cls = {"vit": pa.vit.Attention, "setr": pa.setr.Attention, "moat": pa.moat.Attention, "pvt": pa.pvt.Attention, "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention,
+    cls = {"vit": pa.vit.Attention, "vit_block": pa.vit.TransformerEncoder, "setr": pa.setr.Attention, "moat": pa.moat.Attention, "pvt": pa.pvt.Attention, "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention,
            "cswin_block": pa.cswin.CSWinBlock, "xca": pa.xcit.XCA, "class_attn": pa.xcit.ClassAttention}[spec["variant"]]
     return cls(**spec["ctor"]).state_dict()
 

@@ -277,3 +277,34 @@ def test_fp32_input_is_opt_in_and_matches_the_16bit_path():
     from pytorch_attention_b200 import ops
     t = torch.randn(1003, device="cuda")
     assert torch.equal(ops.cast_f32(t, torch.bfloat16), t.bfloat16()) and torch.equal(ops.cast_f32(t, torch.float16), t.half())
+
+
+def test_vit_block_attention_half_fused_prenorm_and_residual():
+    """ViT.TransformerEncoder's first half, x + attn(layernorm1(x)) (ViT.py:116), as one C-ABI call: LayerNorm kernel, qkv GEMM,
+    attention core, proj GEMM with the residual in its epilogue -- at the BASELINE width against the oracle, and the full block
+    forward (MLP half in torch) in an fp32 model with fp32 activations."""
+    import pytorch_attention_b200 as pa
+    from pytorch_attention_b200 import _lib
+    from oracle import vit_block_attention_half
+    torch.manual_seed(31)
+    blk = pa.vit.TransformerEncoder(768, 12).eval()
+    with torch.no_grad():
+        blk.layernorm1.weight.copy_(1.0 + 0.1 * torch.randn(768))
+        blk.layernorm1.bias.copy_(0.1 * torch.randn(768))
+        for p in blk.parameters():
+            p.copy_(p.half().float())
+    x = torch.randn(3, 197, 768).half()
+    sd = {k: v.float() for k, v in blk.state_dict().items()}
+    ref = vit_block_attention_half(x.float(), sd["layernorm1.weight"], sd["layernorm1.bias"], sd["attn.qkv.weight"], None,
+                                   sd["attn.proj.weight"], sd["attn.proj.bias"], 12)
+    blk = blk.cuda()
+    with torch.no_grad():
+        n0 = _lib.launch_count()
+        y = blk.attention_half(x.cuda())
+        assert _lib.launch_count() - n0 == 4
+        assert rel_fro(y.float().cpu(), ref) < TOL and rel_max(y.float().cpu(), ref) < 2e-3
+        blk.fp32_input = torch.float16
+        full = blk(x.float().cuda())                       # fp32 model, fp32 activations: whole block
+        cpu = blk.float().cpu()
+        want = ref + cpu.mlp(cpu.layernorm2(ref))
+    assert full.dtype == torch.float32 and rel_fro(full.cpu(), want) < 2e-3

@@ -43,13 +43,19 @@ def test_glue_with_oracle_attention_reproduces_reference_model_logits():
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted")
-def test_class_swap_inside_the_reference_model_constructs_and_loads(monkeypatch):
+@pytest.mark.parametrize("level", ["attention", "block"])
+def test_class_swap_inside_the_reference_model_constructs_and_loads(monkeypatch, level):
     import pytorch_attention_b200 as pa
     monkeypatch.syspath_prepend(REF)
     import ViT
-    monkeypatch.setattr(ViT, "Attention", pa.vit.Attention)        # the substitution INTEGRATION.md describes
+    if level == "attention":
+        monkeypatch.setattr(ViT, "Attention", pa.vit.Attention)    # the substitution INTEGRATION.md describes
+    else:
+        monkeypatch.setattr(ViT, "TransformerEncoder", pa.vit.TransformerEncoder)   # whole block: LN + attention + residual fused
     model = ViT.VisionTransformer(**CFG).eval()                    # ViT.py:98 constructs the drop-in with the reference's arguments
     assert all(isinstance(b.attn, pa.vit.Attention) for b in model.blocks)
+    if level == "block":
+        assert all(isinstance(b, pa.vit.TransformerEncoder) for b in model.blocks)
     sd, x, _ = _load()
     model.load_state_dict(sd, strict=True)                         # identical keys and shapes
     with pytest.raises(RuntimeError, match="CPU"):                 # product path: no CPU fallback
