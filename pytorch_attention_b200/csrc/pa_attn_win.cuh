@@ -9,6 +9,9 @@
 // Two single-slot CTAs per SM (256 TMEM columns, <= 113 KB shared memory, 384 threads each): warp 0 TMA | warp 1 MMA | warp 2
 // TMEM allocator | warps 4-11 softmax + epilogue, two threads per query row (see pa_cosched.cuh for why this shape beats the
 // two-slot CTA of attn_core_kernel).  TMEM slot: S fp32 [0, kb) -> fp16 P in place; O fp32 [256 - HD, 256), kb <= 256 - HD.
+// Measured and rejected: the 8 query rows past the last full tile of a 392-token window (3 x 128 + 8) on the CUDA cores, one warp
+// per row, instead of a fourth tensor-core tile -- 1280 vs 1271 us per branch: a tile whose other 120 rows are inactive costs
+// next to nothing, the kernel is bound by the softmax work of the populated rows, not by the number of chains.
 #pragma once
 #include "pa_attn.cuh"
 #include "pa_cosched.cuh"

@@ -10,6 +10,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
 
 #include "../../include/pa_b200.h"
 
@@ -99,6 +100,29 @@ inline int make_tmap_16b(CUtensorMap* out, int dtype, const void* base, int rank
     }
     if (box[i] == 0 || box[i] > 256) return fail(PA_ERR_BAD_SHAPE, "TMA box dim %d = %u out of range", i, box[i]);
   }
+  // Keyed cache (thread-local: no lock, one host thread per GPU is the supported concurrency): a tensor map is a pure function of
+  // these arguments, a forward re-creates the same 8-12 maps every call (same workspace, same weights), and the driver's encoder
+  // costs ~0.4 us each.  The key holds every argument, so a recycled address with another shape is simply another entry.
+  struct Key {
+    const void* base; int dtype, rank, swz; uint64_t dims[5]; uint64_t str[4]; uint32_t box[5];
+    bool operator==(const Key& o) const { return memcmp(this, &o, sizeof(Key)) == 0; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key& k) const {
+      const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+      uint64_t h = 1469598103934665603ull;
+      for (size_t i = 0; i < sizeof(Key) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+      return (size_t)h;
+    }
+  };
+  static_assert(sizeof(Key) % 8 == 0, "Key is hashed word-wise");
+  static thread_local std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+  Key key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.dtype = dtype; key.rank = rank; key.swz = (int)swz;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; if (i > 0) key.str[i - 1] = strides_bytes[i - 1]; }
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return PA_OK; }
   CUresult r = fn(out, dtype == PA_DTYPE_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                        : dtype == PA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                   (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -106,6 +130,8 @@ inline int make_tmap_16b(CUtensorMap* out, int dtype, const void* base, int rank
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
                                      (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);
+  if (cache.size() >= 4096) cache.clear();
+  cache.emplace(key, *out);
   return PA_OK;
 }
 

@@ -63,3 +63,20 @@ def test_aten_port_matches_oracle():
     a = vit_attention(x, wq, bq, wp, bp, 2)
     b = vit_attention_aten(x, wq, bq, wp, bp, 2)
     assert (a - b).abs().max().item() < 1e-5
+
+
+def test_aten_port_matches_oracle_at_baseline_config_1():
+    """The CPU arm of bench.py at BASELINE.json configs[0] exactly (B=2, N=197, dim=768, 12 heads) and with the bench's own
+    parameter generator: the timed port and the oracle agree to fp32 round-off, so the CPU number is a number for the reference's math."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from oracle import vit_attention
+    from oracle.aten_port import vit_attention_aten
+    sd = bench.make_cpu_model()
+    torch.manual_seed(1)
+    x = torch.randn(2, 197, 768).half().float()
+    a = vit_attention(x, sd["qkv.weight"], None, sd["proj.weight"], sd["proj.bias"], 12)
+    b = vit_attention_aten(x, sd["qkv.weight"], None, sd["proj.weight"], sd["proj.bias"], 12)
+    assert (a - b).abs().max().item() <= 2e-6 * max(1.0, a.abs().max().item())
