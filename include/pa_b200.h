@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PA_VERSION 100
+#define PA_VERSION 101
 
 enum { PA_DTYPE_F16 = 0, PA_DTYPE_BF16 = 1, PA_DTYPE_F32 = 2 };
 
@@ -156,9 +156,31 @@ typedef struct {
   const float* sr_scale;     /* [C] sr.1.weight * rsqrt(running_var + eps)  (eval BatchNorm folded) */
   const float* sr_shift;     /* [C] (sr.0.bias - running_mean) * sr_scale + sr.1.bias */
   void* y;                   /* [B,N,C] */
+  /* ---- siblings of the same path; all zero / NULL = plain pvt.Attention */
+  int sr_mode;               /* 0: depthwise conv + eval BatchNorm (pvt.py:67-71, cmt.py:87-91)
+                                1: dense conv k = stride = sr with bias, no norm (segformer.py:27, 38-39), run as a GEMM over
+                                   the non-overlapping sr x sr patches */
+  const void* sr_dense_weight; /* sr_mode 1: [C, sr*sr*C] (dtype), sr.weight [C,C,sr,sr] permuted to (co, u, v, ci) */
+  const float* sr_dense_bias;  /* sr_mode 1: [C] or NULL */
+  const float* rel_pos;      /* cmt.Attention.forward(x, H, W, relative_pos), cmt.py:100: fp32 [H, N, M] added to
+                                q k^T * scale before the softmax (M = key tokens after the reduction), or NULL.
+                                Needs 64-wide heads and M <= 240 */
 } pa_pvt_args;
 size_t pa_pvt_workspace_bytes(const pa_pvt_args* a);
 int pa_pvt_fwd(const pa_pvt_args* a, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- pvt.Block / segformer.Block / cmt.Block, attention half */
+/* y = x + Attention(LayerNorm(x), H, W [, relative_pos])   (pvt.py:106, segformer.py:76, cmt.py:131): this library's LayerNorm
+ * row kernel (fp32 statistics, fp16 output) in front, the residual x added in the epilogue of the proj GEMM.  attn.q_weight
+ * and (sr == 1) attn.kv_weight must be fp16: their input is the fp16 LayerNorm output. */
+typedef struct {
+  pa_pvt_args attn;          /* attn.x = block input, attn.y = x + attention */
+  const float* ln_weight;    /* [C] norm1.weight */
+  const float* ln_bias;      /* [C] norm1.bias */
+  float ln_eps;
+} pa_pvt_block_args;
+size_t pa_pvt_block_attn_workspace_bytes(const pa_pvt_block_args* a);
+int pa_pvt_block_attn_fwd(const pa_pvt_block_args* a, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- cvt.Attention  (cvt.py:48-76), NCHW in and out */
 typedef struct {
@@ -193,6 +215,18 @@ typedef struct {
 } pa_xcit_args;
 size_t pa_xca_workspace_bytes(const pa_xcit_args* a);
 int pa_xca_fwd(const pa_xcit_args* a, void* workspace, size_t workspace_bytes, void* stream);
+/* xcit.XCABlock, attention half (xcit.py:291):  y = x + gamma1 * XCA(LayerNorm(x)).  LayerScale is folded by the caller:
+ * attn.proj_weight = gamma1[:,None] * proj.weight (fp16), attn.proj_bias = gamma1 * proj.bias -- algebraically the same
+ * x + O (gamma1 * Wp)^T + gamma1 * b, so the residual epilogue of the proj GEMM finishes the block.  attn.qkv_weight must be
+ * fp16 (its input is the fp16 LayerNorm output).  Launches: LayerNorm -> GEMM(qkv) -> XCA core -> GEMM(proj + residual). */
+typedef struct {
+  pa_xcit_args attn;         /* attn.x = block input, attn.y = block output of the attention half */
+  const float* ln_weight;    /* [C] norm1.weight */
+  const float* ln_bias;      /* [C] norm1.bias */
+  float ln_eps;
+} pa_xca_block_args;
+size_t pa_xca_block_attn_workspace_bytes(const pa_xca_block_args* a);
+int pa_xca_block_attn_fwd(const pa_xca_block_args* a, void* workspace, size_t workspace_bytes, void* stream);
 size_t pa_class_attn_workspace_bytes(const pa_xcit_args* a);
 int pa_class_attn_fwd(const pa_xcit_args* a, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -77,8 +77,10 @@ def vit_block_attention_half(x, ln_weight, ln_bias, qkv_weight, qkv_bias, proj_w
 def pvt_attention(x, H_img, W_img, q_weight, q_bias, k_weight, k_bias, v_weight, v_bias,
                   proj_weight, proj_bias, num_heads, sr_ratio=1,
                   sr_0_weight=None, sr_0_bias=None, sr_1_weight=None, sr_1_bias=None,
-                  sr_1_running_mean=None, sr_1_running_var=None, bn_eps=1e-5):
+                  sr_1_running_mean=None, sr_1_running_var=None, bn_eps=1e-5, relative_pos=None):
     """pvt.Attention.forward(x, H, W) (pvt.py:73-91), eval-mode BatchNorm.
+    cmt.Attention.forward(x, H, W, relative_pos) (cmt.py:93-111) is the same module with ``relative_pos`` ([heads, N, M],
+    broadcast over the batch) added to the scaled scores before the softmax (cmt.py:100).
 
     K/V tokens: x_[b, i*(W/sr)+j, c] = BN_c( sum_{u,v<sr} w[c,0,u,v] *
     x[b, (sr*i+u)*W + (sr*j+v), c] + bias[c] )   (pvt.py:77-78).
@@ -102,6 +104,55 @@ def pvt_attention(x, H_img, W_img, q_weight, q_bias, k_weight, k_bias, v_weight,
     M = kv_in.shape[1]
     k = _lin(kv_in, k_weight, k_bias).reshape(B, M, nh, hd)
     v = _lin(kv_in, v_weight, v_bias).reshape(B, M, nh, hd)
+    s = torch.einsum("bnhd,bmhd->bhnm", q, k) * scale
+    if relative_pos is not None:
+        s = s + relative_pos                                      # cmt.py:100
+    p = _softmax_last(s)
+    o = torch.einsum("bhnm,bmhd->bnhd", p, v).reshape(B, N, C)
+    return _lin(o, proj_weight, proj_bias)
+
+
+def _layer_norm_rows(x, w, b, eps=1e-5):
+    """nn.LayerNorm over the channel axis: biased variance, eps inside the square root."""
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def pvt_block_attention_half(x, H_img, W_img, norm1_weight, norm1_bias, eps=1e-5, **attn_kw):
+    """First half of pvt.Block.forward (pvt.py:106): x + attn(norm1(x), H, W); attn_kw = pvt_attention's parameters."""
+    return x + pvt_attention(_layer_norm_rows(x, norm1_weight, norm1_bias, eps), H_img, W_img, **attn_kw)
+
+
+# --------------------------------------------------------------------------
+# SegFormer efficient self-attention (reference: segformer.py:17-50)
+# --------------------------------------------------------------------------
+def segformer_attention(x, H_img, W_img, q_weight, q_bias, kv_weight, kv_bias, proj_weight, proj_bias, num_heads,
+                        sr_ratio=1, sr_weight=None, sr_bias=None):
+    """segformer.Attention.forward(x, H, W) (segformer.py:33-50).
+
+    Reduction (segformer.py:38-39): a dense conv with kernel = stride = sr, no norm behind it:
+    x_[b, i*(W/sr)+j, co] = sum_{ci,u,v} w[co,ci,u,v] * x[b, (sr*i+u)*W + (sr*j+v), ci] + bias[co].
+    kv = Linear(C, 2C): output row o -> (k|v, head, d) = (o // C, (o % C) // hd, o % hd)   (segformer.py:40 / 43).
+    """
+    B, N, C = x.shape
+    nh = num_heads
+    hd = C // nh
+    scale = hd ** -0.5
+    q = _lin(x, q_weight, q_bias).reshape(B, N, nh, hd)
+    if sr_ratio > 1:
+        sr = sr_ratio
+        Hs, Ws = H_img // sr, W_img // sr
+        xi = x.reshape(B, H_img, W_img, C)[:, : Hs * sr, : Ws * sr].reshape(B, Hs, sr, Ws, sr, C)
+        t = torch.einsum("biujvc,ocuv->bijo", xi, sr_weight)
+        if sr_bias is not None:
+            t = t + sr_bias
+        kv_in = t.reshape(B, Hs * Ws, C)
+    else:
+        kv_in = x
+    M = kv_in.shape[1]
+    kv = _lin(kv_in, kv_weight, kv_bias).reshape(B, M, 2, nh, hd)
+    k, v = kv[:, :, 0], kv[:, :, 1]
     s = torch.einsum("bnhd,bmhd->bhnm", q, k) * scale
     p = _softmax_last(s)
     o = torch.einsum("bhnm,bmhd->bnhd", p, v).reshape(B, N, C)
@@ -285,3 +336,11 @@ def class_attention(x, qkv_weight, qkv_bias, proj_weight, proj_bias, num_heads, 
     cls = torch.einsum("bhn,bhnd->bhd", a, v).reshape(B, 1, C)   # xcit.py:185
     cls = _lin(cls, proj_weight, proj_bias)
     return torch.cat([cls, x[:, 1:]], dim=1)                     # xcit.py:187
+
+
+def xca_block_attention_half(x, norm1_weight, norm1_bias, gamma1, qkv_weight, qkv_bias, proj_weight, proj_bias, temperature,
+                             num_heads, eps=1e-6):
+    """First line of XCABlock.forward (xcit.py:291): x + gamma1 * attn(norm1(x)).  eps: XCiT builds its blocks with
+    norm_layer = partial(nn.LayerNorm, eps=1e-6); a bare XCABlock uses nn.LayerNorm's 1e-5 -- the caller passes the module's."""
+    h = _layer_norm_rows(x, norm1_weight, norm1_bias, eps)
+    return x + gamma1 * xca_attention(h, qkv_weight, qkv_bias, proj_weight, proj_bias, temperature, num_heads)

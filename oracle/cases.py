@@ -26,6 +26,16 @@ GOLDEN_CASES = {
     # pvt.Attention(dim, num_heads, sr_ratio)            pvt.py:52-91
     "pvt_b2_16x16_c128_h2_sr4": dict(variant="pvt", ctor=dict(dim=128, num_heads=2, sr_ratio=4), x=(2, 256, 128), hw=(16, 16)),
     "pvt_b2_8x8_c128_h2_sr1_bias": dict(variant="pvt", ctor=dict(dim=128, num_heads=2, sr_ratio=1, qkv_bias=True), x=(2, 64, 128), hw=(8, 8)),
+    # pvt.Block, attention half: x + attn(norm1(x), H, W)   pvt.py:93-106
+    "pvtblock_b2_16x16_c128_h2_sr4": dict(variant="pvt_block", ctor=dict(dim=128, num_heads=2, sr_ratio=4), x=(2, 256, 128), hw=(16, 16),
+                                         keep=("norm1.", "attn.")),
+    # segformer.Attention(dim, num_heads, qkv_bias, ..., sr_ratio): dense reduction conv, fused kv    segformer.py:17-50
+    "segformer_b2_16x16_c64_h2_sr4_bias": dict(variant="segformer", ctor=dict(dim=64, num_heads=2, qkv_bias=True, sr_ratio=4), x=(2, 256, 64), hw=(16, 16)),
+    "segformer_b2_16x16_c160_h5_sr2": dict(variant="segformer", ctor=dict(dim=160, num_heads=5, sr_ratio=2), x=(2, 256, 160), hw=(16, 16)),
+    "segformer_b2_8x8_c128_h2_sr1": dict(variant="segformer", ctor=dict(dim=128, num_heads=2, sr_ratio=1), x=(2, 64, 128), hw=(8, 8)),
+    # cmt.Attention(dim, num_heads, sr_ratio).forward(x, H, W, relative_pos)          cmt.py:72-111
+    "cmt_b2_14x14_c64_h1_sr2": dict(variant="cmt", ctor=dict(dim=64, num_heads=1, sr_ratio=2), x=(2, 196, 64), hw=(14, 14)),
+    "cmt_b2_16x16_c128_h2_sr2_bias": dict(variant="cmt", ctor=dict(dim=128, num_heads=2, sr_ratio=2, qkv_bias=True), x=(2, 256, 128), hw=(16, 16)),
     # cvt.Attention(dim, num_heads, ks)                   cvt.py:48-76
     "cvt_b2_c128_h2_14x14": dict(variant="cvt", ctor=dict(dim=128, num_heads=2), x=(2, 128, 14, 14)),
     # cswin.LePEAttention(dim, resolution, idx, split_size, num_heads)   cswin.py:51-127
@@ -38,6 +48,9 @@ GOLDEN_CASES = {
     # xcit.XCA / xcit.ClassAttention                       xcit.py:233-265, 159-188
     "xca_b2_n196_c128_h2": dict(variant="xca", ctor=dict(dim=128, num_heads=2, qkv_bias=True), x=(2, 196, 128)),
     "classattn_b2_n197_c128_h2": dict(variant="class_attn", ctor=dict(dim=128, num_heads=2, qkv_bias=True), x=(2, 197, 128)),
+    # xcit.XCABlock, attention half: x + gamma1 * attn(norm1(x))          xcit.py:267-291
+    "xcablock_b2_n196_c128_h2": dict(variant="xca_block", ctor=dict(dim=128, num_heads=2, qkv_bias=True, eta=1.0), x=(2, 196, 128),
+                                     keep=("norm1.", "attn.", "gamma1")),
 }
 
 _REF_CLASS = {
@@ -46,6 +59,10 @@ _REF_CLASS = {
     "setr": ("setr", "Attention"),
     "moat": ("moat", "Attention"),
     "pvt": ("pvt", "Attention"),
+    "pvt_block": ("pvt", "Block"),
+    "segformer": ("segformer", "Attention"),
+    "cmt": ("cmt", "Attention"),
+    "xca_block": ("xcit", "XCABlock"),
     "cvt": ("cvt", "Attention"),
     "lepe": ("cswin", "LePEAttention"),
     "cswin_block": ("cswin", "CSWinBlock"),
@@ -78,6 +95,8 @@ def randomise_module_(mod, seed):
         for name, p in mod.named_parameters():
             if name.endswith("temperature"):
                 p.copy_(torch.rand(p.shape, generator=g) * 1.5 + 0.5)
+            if name.endswith("gamma1"):
+                p.copy_((torch.rand(p.shape, generator=g) + 0.5) * p)   # LayerScale (xcit.py:285) = eta * ones: spread it so a dropped gamma shows
             if name.endswith(".bias") and "norm" not in name and "sr.1" not in name and "qkv.1" not in name:
                 # default Linear/Conv biases are tiny; widen them a bit so a dropped bias is visible
                 p.copy_(torch.randn(p.shape, generator=g) * 0.05)
@@ -91,13 +110,20 @@ def randomise_module_(mod, seed):
 def make_inputs(spec, seed=0):
     g = torch.Generator().manual_seed(1000 + seed)
     x = torch.randn(spec["x"], generator=g)
-    return {"x": round_fp16_(x)}
+    out = {"x": round_fp16_(x)}
+    if spec["variant"] == "cmt":
+        # the model's relative_pos parameter, [heads, N, N / sr^2] (cmt.py:169-180; zeros at init -- random here)
+        c = spec["ctor"]
+        N = spec["x"][1]
+        M = N // (c.get("sr_ratio", 1) ** 2)
+        out["relative_pos"] = round_fp16_(torch.randn(c["num_heads"], N, M, generator=g))
+    return out
 
 
 def load_reference(ref_path):
     if ref_path not in sys.path:
         sys.path.insert(0, ref_path)
-    return {m: importlib.import_module(m) for m in ("ViT", "pvt", "cvt", "cswin", "xcit", "moat")}
+    return {m: importlib.import_module(m) for m in ("ViT", "pvt", "cvt", "cswin", "xcit", "moat", "segformer", "cmt")}
 
 
 def load_reference_class(ref_path, module, cls):
@@ -116,11 +142,19 @@ def load_reference_class(ref_path, module, cls):
     return ns[cls]
 
 
-def reference_forward(spec, mod, x):
+def reference_forward(spec, mod, x, inputs=None):
     v = spec["variant"]
     with torch.no_grad():
-        if v == "pvt":
+        if v in ("pvt", "segformer"):
             return mod(x, *spec["hw"])
+        if v == "cmt":
+            return mod(x, *spec["hw"], inputs["relative_pos"])
+        if v == "pvt_block":
+            # attention half only (pvt.py:106), with the reference block's own sub-modules
+            return x + mod.attn(mod.norm1(x), *spec["hw"])
+        if v == "xca_block":
+            # first line of XCABlock.forward (xcit.py:291)
+            return x + mod.gamma1 * mod.attn(mod.norm1(x))
         if v == "cswin_block":
             # attention half only (cswin.py:184-194): x + proj(attn(norm1(x)))
             return cswin_block_attention_half_reference(mod, x)
@@ -151,8 +185,9 @@ def build_reference_case(spec, ref_path, seed=0):
     mod = load_reference_class(ref_path, modname, clsname)(**spec["ctor"]).eval()
     randomise_module_(mod, seed + 7)
     inputs = make_inputs(spec, seed)
-    y = reference_forward(spec, mod, inputs["x"]).float()
-    params = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    y = reference_forward(spec, mod, inputs["x"], inputs).float()
+    keep = spec.get("keep")           # block cases: only the attention half's parameters are stored
+    params = {k: v.detach().clone() for k, v in mod.state_dict().items() if keep is None or k.startswith(tuple(keep))}
     return {"inputs": inputs, "params": params, "y_ref": y, "module": mod}
 
 
@@ -179,6 +214,25 @@ def run_oracle_case(spec, inputs, params, dtype=torch.float32):
                  "sr.0.weight", "sr.0.bias", "sr.1.weight", "sr.1.bias", "sr.1.running_mean", "sr.1.running_var")
         return A.pvt_attention(x, spec["hw"][0], spec["hw"][1], num_heads=c["num_heads"],
                                sr_ratio=c.get("sr_ratio", 1), **kw)
+    if v == "pvt_block":
+        keys = ("q.weight", "q.bias", "k.weight", "k.bias", "v.weight", "v.bias", "proj.weight", "proj.bias",
+                "sr.0.weight", "sr.0.bias", "sr.1.weight", "sr.1.bias", "sr.1.running_mean", "sr.1.running_var")
+        kw = {k.replace(".", "_"): P.get("attn." + k) for k in keys}
+        return A.pvt_block_attention_half(x, spec["hw"][0], spec["hw"][1], P["norm1.weight"], P["norm1.bias"],
+                                          num_heads=c["num_heads"], sr_ratio=c.get("sr_ratio", 1), **kw)
+    if v == "cmt":
+        kw = _kw(P, "q.weight", "q.bias", "k.weight", "k.bias", "v.weight", "v.bias", "proj.weight", "proj.bias",
+                 "sr.0.weight", "sr.0.bias", "sr.1.weight", "sr.1.bias", "sr.1.running_mean", "sr.1.running_var")
+        return A.pvt_attention(x, spec["hw"][0], spec["hw"][1], num_heads=c["num_heads"], sr_ratio=c.get("sr_ratio", 1),
+                               relative_pos=inputs["relative_pos"].to(dtype), **kw)
+    if v == "segformer":
+        return A.segformer_attention(x, spec["hw"][0], spec["hw"][1], P["q.weight"], P.get("q.bias"), P["kv.weight"], P.get("kv.bias"),
+                                     P["proj.weight"], P["proj.bias"], c["num_heads"], c.get("sr_ratio", 1),
+                                     P.get("sr.weight"), P.get("sr.bias"))
+    if v == "xca_block":
+        return A.xca_block_attention_half(x, P["norm1.weight"], P["norm1.bias"], P["gamma1"], P["attn.qkv.weight"],
+                                          P.get("attn.qkv.bias"), P["attn.proj.weight"], P["attn.proj.bias"],
+                                          P["attn.temperature"], c["num_heads"], eps=1e-5)
     if v == "cvt":
         kw = _kw(P, "conv_proj_qkv.0.weight", "conv_proj_qkv.0.bias", "conv_proj_qkv.1.weight",
                  "conv_proj_qkv.1.bias", "conv_proj_qkv.1.running_mean", "conv_proj_qkv.1.running_var",

@@ -49,7 +49,12 @@ class PvtArgs(C.Structure):
                 ("Himg", _i), ("Wimg", _i), ("sr", _i), ("scale", _f),
                 ("x", _vp), ("q_weight", _vp), ("q_bias", _vp), ("kv_weight", _vp), ("kv_bias", _vp),
                 ("proj_weight", _vp), ("proj_bias", _vp), ("sr_weight_t", _vp), ("sr_scale", _vp), ("sr_shift", _vp),
-                ("y", _vp)]
+                ("y", _vp),
+                ("sr_mode", _i), ("sr_dense_weight", _vp), ("sr_dense_bias", _vp), ("rel_pos", _vp)]
+
+
+class PvtBlockArgs(C.Structure):
+    _fields_ = [("attn", PvtArgs), ("ln_weight", _vp), ("ln_bias", _vp), ("ln_eps", _f)]
 
 
 class CvtArgs(C.Structure):
@@ -63,6 +68,10 @@ class XcitArgs(C.Structure):
     _fields_ = [("dtype", _i), ("out_dtype", _i), ("B", _i), ("N", _i), ("C", _i), ("H", _i), ("scale", _f),
                 ("x", _vp), ("qkv_weight", _vp), ("qkv_bias", _vp), ("proj_weight", _vp), ("proj_bias", _vp),
                 ("temperature", _vp), ("y", _vp)]
+
+
+class XcaBlockArgs(C.Structure):
+    _fields_ = [("attn", XcitArgs), ("ln_weight", _vp), ("ln_bias", _vp), ("ln_eps", _f)]
 
 
 class LepeArgs(C.Structure):
@@ -101,10 +110,14 @@ SYMBOLS = {
     "pa_vit_block_attn_fwd": (_i, [C.POINTER(VitBlockArgs), _vp, C.c_size_t, _vp]),
     "pa_pvt_workspace_bytes": (C.c_size_t, [C.POINTER(PvtArgs)]),
     "pa_pvt_fwd": (_i, [C.POINTER(PvtArgs), _vp, C.c_size_t, _vp]),
+    "pa_pvt_block_attn_workspace_bytes": (C.c_size_t, [C.POINTER(PvtBlockArgs)]),
+    "pa_pvt_block_attn_fwd": (_i, [C.POINTER(PvtBlockArgs), _vp, C.c_size_t, _vp]),
     "pa_cvt_workspace_bytes": (C.c_size_t, [C.POINTER(CvtArgs)]),
     "pa_cvt_fwd": (_i, [C.POINTER(CvtArgs), _vp, C.c_size_t, _vp]),
     "pa_xca_workspace_bytes": (C.c_size_t, [C.POINTER(XcitArgs)]),
     "pa_xca_fwd": (_i, [C.POINTER(XcitArgs), _vp, C.c_size_t, _vp]),
+    "pa_xca_block_attn_workspace_bytes": (C.c_size_t, [C.POINTER(XcaBlockArgs)]),
+    "pa_xca_block_attn_fwd": (_i, [C.POINTER(XcaBlockArgs), _vp, C.c_size_t, _vp]),
     "pa_class_attn_workspace_bytes": (C.c_size_t, [C.POINTER(XcitArgs)]),
     "pa_class_attn_fwd": (_i, [C.POINTER(XcitArgs), _vp, C.c_size_t, _vp]),
     "pa_cswin_lepe_fwd": (_i, [C.POINTER(LepeArgs), _vp]),

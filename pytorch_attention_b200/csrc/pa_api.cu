@@ -302,6 +302,7 @@ struct AttnLaunch {
   float scale;
   int B, R, H_sp, W_sp;   // windowed: images, resolution, window shape
   int add_into_out;
+  const float* rel_pos;   // additive score bias [H, n_q, n_k] fp32 before the softmax (cmt.py:100), or nullptr
 };
 
 template <int HD, bool WIN>
@@ -342,6 +343,7 @@ int attn_prepare(const AttnLaunch& a, AttnPlan* plan) {
   p.O = a.o; p.ldo = a.ldo; p.o_group = a.o_group; p.o_col0 = a.o_col0;
   p.scale_log2e = a.scale * 1.4426950408889634f;
   p.add_into_out = a.add_into_out;
+  p.rel_pos = a.rel_pos; p.rel_mul = 1.f / a.scale;
   p.trace = g_gemm_trace;
   p.debug_flags = env().attn_debug;
   if (!a.windowed) {
@@ -461,6 +463,7 @@ int launch_attn_single_slot(const AttnPlan& plan, cudaStream_t st);   // below (
 
 int attn_launch(const AttnLaunch& a, cudaStream_t st) {
   if (attn_wide_hd(a.hd)) {
+    if (a.rel_pos) return fail(PA_ERR_UNSUPPORTED, "attention core with relative_pos: needs 64-wide heads (got %d)", a.hd);
     if (a.windowed) return fail(PA_ERR_UNSUPPORTED, "windowed attention: head_dim %d unsupported (32 or 64)", a.hd);
     if (!(a.scale > 0.f)) return fail(PA_ERR_UNSUPPORTED, "attention core: scale must be > 0");
     if (a.ldo % 8 || a.o_col0 % 8 || a.o_group % 8 || (reinterpret_cast<uintptr_t>(a.o) & 15))
@@ -483,6 +486,12 @@ int attn_launch(const AttnLaunch& a, cudaStream_t st) {
   int rc = attn_prepare(a, &plan);
   if (rc) return rc;
   const int hd = a.hd;
+  if (a.rel_pos) {
+    // the score bias exists in the single-slot kernel only: 64-wide heads, at most 240 keys
+    if (hd != 64 || a.windowed || plan.p.nkb != 1 || !plan.p.tma_store || plan.p.kb > 240)
+      return fail(PA_ERR_UNSUPPORTED, "attention core with relative_pos: needs 64-wide heads and at most 240 keys (got head_dim %d, %d keys)", hd, a.n_k);
+    return launch_attn_single_slot(plan, st);
+  }
   // 64-wide heads, one key block, staged output: two single-slot CTAs per SM (pa_cosched.cuh's attention role as a kernel)
   if (hd == 64 && !a.windowed && plan.p.nkb == 1 && plan.p.tma_store && plan.p.kb <= 240 && !env().attn_two_slot)
     return launch_attn_single_slot(plan, st);
@@ -492,13 +501,14 @@ int attn_launch(const AttnLaunch& a, cudaStream_t st) {
                     : launch_attn_t<32, false>(plan.tq, plan.tk, plan.tv, plan.to, plan.p, plan.smem, st);
 }
 
-int launch_attn_single_slot(const AttnPlan& plan, cudaStream_t st) {
+template <bool RELPOS>
+int launch_attn_single_slot_t(const AttnPlan& plan, cudaStream_t st) {
   CsParams cp = {};
   cp.at = plan.p;
   cp.at.wait_ctr = nullptr; cp.at.signal_ctr = nullptr;
   const int smem = cs_attn_bar_offset(plan.p.kb) + 1024;
   static SmemAttr smem_attr;
-  int rc = smem_attr.ensure(attn_single_slot_kernel, smem);
+  int rc = smem_attr.ensure(attn_single_slot_kernel<RELPOS>, smem);
   if (rc) return rc;
   {
     static std::mutex mu;
@@ -507,16 +517,19 @@ int launch_attn_single_slot(const AttnPlan& plan, cudaStream_t st) {
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(mu);
     if (!carve[dev & 63]) {
-      PA_CUDA_OK(cudaFuncSetAttribute(attn_single_slot_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      PA_CUDA_OK(cudaFuncSetAttribute(attn_single_slot_kernel<RELPOS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       carve[dev & 63] = true;
     }
   }
   const int units = plan.p.G * plan.p.H * plan.p.q_tiles;
   const int cap = 2 * num_sms();
-  attn_single_slot_kernel<<<units < cap ? units : cap, CS_THREADS, smem, st>>>(plan.tq, plan.tk, plan.tv, plan.to, cp);
+  attn_single_slot_kernel<RELPOS><<<units < cap ? units : cap, CS_THREADS, smem, st>>>(plan.tq, plan.tk, plan.tv, plan.to, cp);
   PA_CUDA_OK(cudaGetLastError());
   launch_counter()++;
   return PA_OK;
+}
+int launch_attn_single_slot(const AttnPlan& plan, cudaStream_t st) {
+  return plan.p.rel_pos ? launch_attn_single_slot_t<true>(plan, st) : launch_attn_single_slot_t<false>(plan, st);
 }
 
 int attn_impl(const pa_attn_args* a, cudaStream_t st) {
@@ -1023,21 +1036,28 @@ static int pvt_check(const pa_pvt_args* a) {
 }
 static inline int pvt_m(const pa_pvt_args* a) { return a->sr > 1 ? (a->Himg / a->sr) * (a->Wimg / a->sr) : a->N; }
 
-size_t pa_pvt_workspace_bytes(const pa_pvt_args* a) {
-  if (pvt_check(a)) return 0;
-  const size_t rows = (size_t)a->B * a->N, mrows = (size_t)a->B * pvt_m(a);
-  return align_up(mrows * a->C * 2, 1024) + align_up(rows * a->C * 2, 1024) * 2 + align_up(mrows * 2 * a->C * 2, 1024) + 1024;
-}
-
-int pa_pvt_fwd(const pa_pvt_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+static int pvt_check_full(const pa_pvt_args* a) {
   int rc = pvt_check(a);
   if (rc) return rc;
-  if (!a->x || !a->q_weight || !a->kv_weight || !a->proj_weight || !a->y) return fail(PA_ERR_NULL, "pa_pvt_fwd: x/weights/y must be non-NULL");
-  if (a->sr > 1 && (!a->sr_weight_t || !a->sr_scale || !a->sr_shift)) return fail(PA_ERR_NULL, "pa_pvt_fwd: sr_ratio>1 needs sr_weight_t/sr_scale/sr_shift");
-  const size_t need = pa_pvt_workspace_bytes(a);
-  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_pvt_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
-  if ((rc = current_device_check())) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
+  if (a->sr_mode != 0 && a->sr_mode != 1) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: sr_mode must be 0 (depthwise + BatchNorm) or 1 (dense conv)");
+  if (a->sr > 1 && (a->Himg % a->sr || a->Wimg % a->sr))
+    return fail(PA_ERR_BAD_SHAPE, "pa_pvt: H=%d, W=%d not divisible by sr_ratio %d", a->Himg, a->Wimg, a->sr);
+  return PA_OK;
+}
+
+size_t pa_pvt_workspace_bytes(const pa_pvt_args* a) {
+  if (pvt_check_full(a)) return 0;
+  const size_t rows = (size_t)a->B * a->N, mrows = (size_t)a->B * pvt_m(a);
+  // reduced map, q, attention output, [k|v], and (dense reduction) the patch matrix = a re-partition of x
+  return align_up(mrows * a->C * 2, 1024) + align_up(rows * a->C * 2, 1024) * 2 + align_up(mrows * 2 * a->C * 2, 1024) +
+         ((a->sr > 1 && a->sr_mode == 1) ? align_up(rows * a->C * 2, 1024) : 0) + 1024;
+}
+
+// [sr] -> q GEMM -> [k|v] GEMM -> attention core -> proj GEMM (+ residual in its epilogue).  x_in / x_dtype: the operand of the
+// q projection and of the reduction (a->x, or the LayerNorm output of the block entry point); residual: nullptr or the tensor
+// added to proj's result (dtype a->dtype, pitch C).  ws: pa_pvt_workspace_bytes(a) bytes.
+static int pvt_run(const pa_pvt_args* a, const void* x_in, int x_dtype, const void* residual, void* workspace, cudaStream_t st) {
+  int rc;
   const int C = a->C, M = pvt_m(a);
   const long long rows = (long long)a->B * a->N, mrows = (long long)a->B * M;
   Arena ws(workspace);
@@ -1045,22 +1065,35 @@ int pa_pvt_fwd(const pa_pvt_args* a, void* workspace, size_t workspace_bytes, vo
   void* qb = ws.take((size_t)rows * C * 2);
   void* ob = ws.take((size_t)rows * C * 2);
   void* kv = ws.take((size_t)mrows * 2 * C * 2);
-  const void* kv_in = a->x;
-  int kv_dtype = a->dtype;
-  if (a->sr > 1) {
-    // spatial reduction: depthwise conv (k = stride = sr) + eval BatchNorm folded into scale/shift   (pvt.py:77-78)
+  const void* kv_in = x_in;
+  int kv_dtype = x_dtype;
+  if (a->sr > 1 && a->sr_mode == 0) {
+    // spatial reduction: depthwise conv (k = stride = sr) + eval BatchNorm folded into scale/shift   (pvt.py:77-78, cmt.py:97-98)
     SrParams sp;
-    sp.x = a->x; sp.out = xr; sp.w = a->sr_weight_t; sp.scale = a->sr_scale; sp.shift = a->sr_shift;
+    sp.x = x_in; sp.out = xr; sp.w = a->sr_weight_t; sp.scale = a->sr_scale; sp.shift = a->sr_shift;
     sp.B = a->B; sp.H = a->Himg; sp.W = a->Wimg; sp.C = C; sp.sr = a->sr; sp.Hs = a->Himg / a->sr; sp.Ws = a->Wimg / a->sr;
-    sp.dtype = a->dtype;
+    sp.dtype = x_dtype;
     sr_conv_bn_kernel<<<grid_for(mrows * (C / 8), 256), 256, 0, st>>>(sp);
     PA_CUDA_OK(cudaGetLastError());
     launch_counter()++;
     kv_in = xr;
     kv_dtype = PA_DTYPE_F16;
+  } else if (a->sr > 1) {
+    // spatial reduction: dense conv k = stride = sr (segformer.py:38-39) = GEMM over the sr x sr patches, K = sr*sr*C
+    void* patches = ws.take((size_t)rows * C * 2);
+    PatchParams pp;
+    pp.x = x_in; pp.out = patches; pp.B = a->B; pp.H = a->Himg; pp.W = a->Wimg; pp.C = C; pp.sr = a->sr;
+    pp.Hs = a->Himg / a->sr; pp.Ws = a->Wimg / a->sr;
+    sr_patchify_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, st>>>(pp);
+    PA_CUDA_OK(cudaGetLastError());
+    launch_counter()++;
+    const int Kd = a->sr * a->sr * C;
+    if ((rc = linear(patches, x_dtype, Kd, a->sr_dense_weight, x_dtype, a->sr_dense_bias, xr, PA_DTYPE_F16, C, mrows, C, Kd, st))) return rc;
+    kv_in = xr;
+    kv_dtype = PA_DTYPE_F16;
   }
-  // q = x Wq^T (+b)  (pvt.py:75);  [k|v] = x_ [Wk;Wv]^T (+b)  (pvt.py:79-80 / 82-83)
-  if ((rc = linear(a->x, a->dtype, C, a->q_weight, a->dtype, a->q_bias, qb, PA_DTYPE_F16, C, rows, C, C, st))) return rc;
+  // q = x Wq^T (+b)  (pvt.py:75);  [k|v] = x_ [Wk;Wv]^T (+b)  (pvt.py:79-80 / 82-83, segformer.py:40 / 43)
+  if ((rc = linear(x_in, x_dtype, C, a->q_weight, x_dtype, a->q_bias, qb, PA_DTYPE_F16, C, rows, C, C, st))) return rc;
   if ((rc = linear(kv_in, kv_dtype, C, a->kv_weight, kv_dtype, a->kv_bias, kv, PA_DTYPE_F16, 2 * C, mrows, 2 * C, C, st))) return rc;
   AttnLaunch at = {};
   at.hd = C / a->H; at.G = a->B; at.H = a->H; at.n_q = a->N; at.n_k = M;
@@ -1068,8 +1101,58 @@ int pa_pvt_fwd(const pa_pvt_args* a, void* workspace, size_t workspace_bytes, vo
   at.k = kv; at.v = kv; at.ldk = 2 * C; at.k_group = (long long)M * 2 * C; at.k_col0 = 0; at.v_col0 = C;
   at.o = ob; at.ldo = C; at.o_group = (long long)a->N * C; at.o_col0 = 0;
   at.scale = a->scale;
+  at.rel_pos = a->rel_pos;                  // cmt.py:100
   if ((rc = attn_launch(at, st))) return rc;
-  return linear(ob, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st);
+  return linear(ob, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st,
+                residual, C, a->dtype);
+}
+
+static int pvt_ptr_check(const pa_pvt_args* a, const char* who) {
+  if (!a->x || !a->q_weight || !a->kv_weight || !a->proj_weight || !a->y) return fail(PA_ERR_NULL, "%s: x/weights/y must be non-NULL", who);
+  if (a->sr > 1 && a->sr_mode == 0 && (!a->sr_weight_t || !a->sr_scale || !a->sr_shift))
+    return fail(PA_ERR_NULL, "%s: sr_ratio>1 needs sr_weight_t/sr_scale/sr_shift", who);
+  if (a->sr > 1 && a->sr_mode == 1 && !a->sr_dense_weight) return fail(PA_ERR_NULL, "%s: sr_mode 1 needs sr_dense_weight", who);
+  return PA_OK;
+}
+
+int pa_pvt_fwd(const pa_pvt_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = pvt_check_full(a);
+  if (rc) return rc;
+  if ((rc = pvt_ptr_check(a, "pa_pvt_fwd"))) return rc;
+  const size_t need = pa_pvt_workspace_bytes(a);
+  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_pvt_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+  if ((rc = current_device_check())) return rc;
+  return pvt_run(a, a->x, a->dtype, nullptr, workspace, (cudaStream_t)stream);
+}
+
+// ================================================================ pvt.Block / segformer.Block / cmt.Block, attention half
+size_t pa_pvt_block_attn_workspace_bytes(const pa_pvt_block_args* b) {
+  if (!b || pvt_check_full(&b->attn)) return 0;
+  return align_up((size_t)b->attn.B * b->attn.N * b->attn.C * 2, 1024) + pa_pvt_workspace_bytes(&b->attn);
+}
+
+int pa_pvt_block_attn_fwd(const pa_pvt_block_args* b, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!b) return fail(PA_ERR_NULL, "pa_pvt_block_attn_fwd: args is NULL");
+  const pa_pvt_args* a = &b->attn;
+  int rc = pvt_check_full(a);
+  if (rc) return rc;
+  if ((rc = pvt_ptr_check(a, "pa_pvt_block_attn_fwd"))) return rc;
+  if (!b->ln_weight || !b->ln_bias) return fail(PA_ERR_NULL, "pa_pvt_block_attn_fwd: ln_weight/ln_bias must be non-NULL");
+  const size_t need = pa_pvt_block_attn_workspace_bytes(b);
+  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_pvt_block_attn_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+  if ((rc = current_device_check())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long rows = (long long)a->B * a->N;
+  Arena ws(workspace);
+  void* img = ws.take((size_t)rows * a->C * 2);
+  // img = norm1(x)   (pvt.py:106, segformer.py:76, cmt.py:131), fp16
+  LnParams ln;
+  ln.x = a->x; ln.out = img; ln.gamma = b->ln_weight; ln.beta = b->ln_bias; ln.rows = rows; ln.C = a->C; ln.dtype = a->dtype; ln.eps = b->ln_eps;
+  layernorm_kernel<<<(int)((rows * 32 + 255) / 256), 256, 0, st>>>(ln);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  // x + proj(attention(img)): the residual rides in the proj GEMM's epilogue
+  return pvt_run(a, img, PA_DTYPE_F16, a->x, ws.take(0), st);
 }
 
 // ================================================================ CvT  (cvt.py:48-76)
@@ -1153,20 +1236,15 @@ size_t pa_xca_workspace_bytes(const pa_xcit_args* a) {
   return align_up(rows * 3 * a->C * 2, 1024) + align_up(rows * a->C * 2, 1024) + 1024;
 }
 
-int pa_xca_fwd(const pa_xcit_args* a, void* workspace, size_t workspace_bytes, void* stream) {
-  int rc = xc_check(a, "pa_xca");
-  if (rc) return rc;
-  if (!a->x || !a->qkv_weight || !a->proj_weight || !a->temperature || !a->y) return fail(PA_ERR_NULL, "pa_xca_fwd: x/weights/temperature/y must be non-NULL");
-  const size_t need = pa_xca_workspace_bytes(a);
-  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_xca_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
-  if ((rc = current_device_check())) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
+// qkv GEMM -> cross-covariance core -> proj GEMM (+ residual).  x_in: the qkv GEMM's operand (a->x or the LayerNorm output).
+static int xca_run(const pa_xcit_args* a, const void* x_in, int x_dtype, const void* residual, void* workspace, cudaStream_t st) {
+  int rc;
   const int C = a->C;
   const long long rows = (long long)a->B * a->N;
   Arena ws(workspace);
   void* qkv = ws.take((size_t)rows * 3 * C * 2);
   void* ob = ws.take((size_t)rows * C * 2);
-  if ((rc = linear(a->x, a->dtype, C, a->qkv_weight, a->dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
+  if ((rc = linear(x_in, x_dtype, C, a->qkv_weight, x_dtype, a->qkv_bias, qkv, PA_DTYPE_F16, 3 * C, rows, 3 * C, C, st))) return rc;
   // cross-covariance core on the tensor cores (pa_xca.cuh): one unit per (image, 128-channel group)
   {
     CUtensorMap tm;
@@ -1193,7 +1271,47 @@ int pa_xca_fwd(const pa_xcit_args* a, void* workspace, size_t workspace_bytes, v
     PA_CUDA_OK(cudaGetLastError());
     launch_counter()++;
   }
-  return linear(ob, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st);
+  return linear(ob, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st,
+                residual, C, a->dtype);
+}
+
+int pa_xca_fwd(const pa_xcit_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = xc_check(a, "pa_xca");
+  if (rc) return rc;
+  if (!a->x || !a->qkv_weight || !a->proj_weight || !a->temperature || !a->y) return fail(PA_ERR_NULL, "pa_xca_fwd: x/weights/temperature/y must be non-NULL");
+  const size_t need = pa_xca_workspace_bytes(a);
+  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_xca_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+  if ((rc = current_device_check())) return rc;
+  return xca_run(a, a->x, a->dtype, nullptr, workspace, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- xcit.XCABlock, attention half (xcit.py:291)
+size_t pa_xca_block_attn_workspace_bytes(const pa_xca_block_args* b) {
+  if (!b || xc_check(&b->attn, "pa_xca_block_attn")) return 0;
+  return align_up((size_t)b->attn.B * b->attn.N * b->attn.C * 2, 1024) + pa_xca_workspace_bytes(&b->attn);
+}
+
+int pa_xca_block_attn_fwd(const pa_xca_block_args* b, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!b) return fail(PA_ERR_NULL, "pa_xca_block_attn_fwd: args is NULL");
+  const pa_xcit_args* a = &b->attn;
+  int rc = xc_check(a, "pa_xca_block_attn");
+  if (rc) return rc;
+  if (!a->x || !a->qkv_weight || !a->proj_weight || !a->temperature || !a->y || !b->ln_weight || !b->ln_bias)
+    return fail(PA_ERR_NULL, "pa_xca_block_attn_fwd: x/weights/temperature/y/ln_weight/ln_bias must be non-NULL");
+  if (a->C % 8) return fail(PA_ERR_BAD_SHAPE, "pa_xca_block_attn_fwd: dim must be a multiple of 8");
+  const size_t need = pa_xca_block_attn_workspace_bytes(b);
+  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_xca_block_attn_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+  if ((rc = current_device_check())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long rows = (long long)a->B * a->N;
+  Arena ws(workspace);
+  void* img = ws.take((size_t)rows * a->C * 2);
+  LnParams ln;
+  ln.x = a->x; ln.out = img; ln.gamma = b->ln_weight; ln.beta = b->ln_bias; ln.rows = rows; ln.C = a->C; ln.dtype = a->dtype; ln.eps = b->ln_eps;
+  layernorm_kernel<<<(int)((rows * 32 + 255) / 256), 256, 0, st>>>(ln);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  return xca_run(a, img, PA_DTYPE_F16, a->x, ws.take(0), st);
 }
 
 size_t pa_class_attn_workspace_bytes(const pa_xcit_args* a) {

@@ -53,6 +53,10 @@ struct AttnParams {
   int* signal_ctr;      // after a (head, query tile) of group g has been stored completely: signal_ctr[g] += 1
   int cta_shift;        // fused kernels: CTA c walks the item sequence of virtual CTA (c - cta_shift) mod grid, so that the
                         // CTAs holding this phase's remainder items are not the ones holding the other phases' remainders
+  // additive score bias before the softmax (cmt.py:100: q k^T * scale + relative_pos): fp32 [H, n_q, n_k], or nullptr.
+  // Single-slot kernel only.  rel_mul = 1 / scale, so that (s + r * rel_mul) * scale == s * scale + r.
+  const float* rel_pos;
+  float rel_mul;
 };
 
 #define ATTN_TRACE(seq, slot_) do { if (p.trace != nullptr && blockIdx.x == 0 && (seq) < 32) p.trace[(seq) * 16 + (slot_)] = clock64(); } while (0)

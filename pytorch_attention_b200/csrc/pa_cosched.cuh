@@ -302,6 +302,7 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
 
 // ================================================================================================ role A
 // unit = (image g, head h, 128-row query tile qt); one 256-column TMEM slot: S fp32 [0, kb) -> P fp16 in place; O fp32 [192, 256)
+template <bool RELPOS>
 __device__ __forceinline__ void cs_attn_role(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                                              const CUtensorMap& tmO, const CsParams& P, uint8_t* smem, uint64_t* bars,
                                              uint32_t tmem_base, int worker, int nworkers) {
@@ -467,6 +468,31 @@ __device__ __forceinline__ void cs_attn_role(const CUtensorMap& tmQ, const CUten
       if (tracer) CS_TRACE_A(it, 2);
       // ---- pass 1: partial row max
       float mx = -INFINITY;
+      // additive score bias (RELPOS, cmt.py:100): this thread's row of rel_pos[h], columns from c_lo on, pre-multiplied by
+      // 1 / scale when it is added to the raw scores -- both passes then run unchanged on s + r / scale
+      const float* rp = nullptr;
+      if constexpr (RELPOS) {
+        const int h = (u / p.q_tiles) % p.H;
+        const int row = min(qt * 128 + trow, p.n_q - 1);
+        rp = p.rel_pos + ((size_t)h * p.n_q + row) * p.n_k + c_lo;
+      }
+      if constexpr (RELPOS) {
+        if (warp_active) {
+#pragma unroll 1
+          for (int k = 0; k < nst; ++k) {
+            uint32_t v[16];
+            float r[16];
+            const int nv = nvalid - k * 16;
+            tmem_ld16(t_my + k * 16, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = (i < nv) ? __ldg(rp + k * 16 + i) * p.rel_mul : 0.f;
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + r[i]);
+            mx = chunk_max<16>(v, nv, mx);
+          }
+        }
+      } else
       if (warp_active) {
         int k = 0;
 #pragma unroll 1
@@ -501,7 +527,17 @@ __device__ __forceinline__ void cs_attn_role(const CUtensorMap& tmQ, const CUten
 #pragma unroll 1
         for (int k = 0; k < nst; ++k) {
           tmem_ld16(t_my + k * 16, va);
-          tmem_ld_wait();
+          if constexpr (RELPOS) {
+            float r[16];
+            const int nv = nvalid - k * 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = (i < nv) ? __ldg(rp + k * 16 + i) * p.rel_mul : 0.f;
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) + r[i]);
+          } else {
+            tmem_ld_wait();
+          }
           exp_stage(va, e, nvalid - k * 16, sl2, mxs);
           pack_stage(e, pk, s0, s1);
           tmem_st8(t_my + k * 8, pk);
@@ -654,7 +690,7 @@ vit_cosched_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   } else if (role == 0) {
     if (!(P.debug & 2)) cs_gemm_role(tmA1, tmB1, tmD1, tmA2, tmB2, tmD2, P, smem, bars, tmem_base, cworker, nclusters_role, crank);
   } else {
-    if (!(P.debug & 1)) cs_attn_role(tmQ, tmK, tmV, tmO, P, smem, bars, tmem_base, cworker * 2 + crank, nclusters_role * 2);
+    if (!(P.debug & 1)) cs_attn_role<false>(tmQ, tmK, tmV, tmO, P, smem, bars, tmem_base, cworker * 2 + crank, nclusters_role * 2);
   }
 
   tc_fence_before();
@@ -670,6 +706,8 @@ vit_cosched_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
 
 // The attention role as a kernel of its own (no GEMM role, no dependency counters): two single-slot CTAs per SM instead of the
 // two-slot CTA of attn_core_kernel.  Used for 64-wide heads with a single key block (ViT / PVT / CvT three-launch paths).
+// RELPOS: an additive fp32 score bias [H, n_q, n_k] before the softmax (cmt.Attention, cmt.py:100).
+template <bool RELPOS>
 __global__ void __launch_bounds__(CS_THREADS, 2)
 attn_single_slot_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const CsParams P) {
@@ -695,7 +733,7 @@ attn_single_slot_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  cs_attn_role(tmQ, tmK, tmV, tmO, P, smem, bars, tmem_base, (int)blockIdx.x, (int)gridDim.x);
+  cs_attn_role<RELPOS>(tmQ, tmK, tmV, tmO, P, smem, bars, tmem_base, (int)blockIdx.x, (int)gridDim.x);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

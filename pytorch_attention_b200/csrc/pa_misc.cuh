@@ -80,6 +80,31 @@ __global__ void sr_conv_bn_kernel(const SrParams p) {
   }
 }
 
+// SegFormer spatial reduction (segformer.py:27, 38-39): a DENSE conv with k = stride = sr is a GEMM over non-overlapping
+// patches.  This kernel lays the patches out as that GEMM's K-major A operand -- a pure re-partition of x (kernel == stride:
+// every element of x moves exactly once):  out[b, i*Ws+j, (u*sr+v)*C + c] = x[b, (sr*i+u)*W + sr*j+v, c]
+// One thread = 8 consecutive channels (16 bytes) of one (output token, tap).
+struct PatchParams {
+  const void* x; void* out;        // x [B, H*W, C], out [B*Hs*Ws, sr*sr*C], same 16-bit dtype
+  int B, H, W, C, sr, Hs, Ws;
+};
+__global__ void sr_patchify_kernel(const PatchParams p) {
+  const int cvec = p.C / 8, taps = p.sr * p.sr;
+  const long long total = (long long)p.B * p.Hs * p.Ws * taps * cvec;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvec);
+    long long t = idx / cvec;
+    const int tap = (int)(t % taps); t /= taps;
+    const int j = (int)(t % p.Ws); t /= p.Ws;
+    const int i = (int)(t % p.Hs);
+    const int b = (int)(t / p.Hs);
+    const int u = tap / p.sr, v = tap - u * p.sr;
+    const long long src = ((long long)b * p.H * p.W + (long long)(p.sr * i + u) * p.W + p.sr * j + v) * p.C + cv * 8;
+    reinterpret_cast<uint4*>(p.out)[idx] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) + src));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // CvT front-end (cvt.py:55-57, 66): depthwise ks x ks conv (stride 1, zero pad) + eval BatchNorm on an NCHW map,
 // written TOKEN-major [B, H*W, C] fp16 so the 1x1 qkv conv becomes a plain K-major GEMM.

@@ -68,16 +68,9 @@ class Attention(StagedModule):
             return d
         return self._stage.get(("w", dtype), srcs, build)
 
-    def forward(self, x, H, W):
-        x, y_dtype = self._prepare_input(x)
-        check_forward_mode(self, x, (self.attn_drop.p, self.proj_drop.p))
-        if self.sr_ratio > 1 and self.training:
-            raise NotImplementedError("train-mode BatchNorm (batch statistics) is not implemented: call .eval()")
+    def _fill(self, a, x, y, H, W, s):
+        """Fill a PvtArgs for this module's parameters (shared by the stand-alone forward and the Block entry point)."""
         B, N, C = x.shape
-        x = x.contiguous()
-        s = self._staged(x.dtype)
-        y = torch.empty(B, N, C, dtype=self.out_dtype or y_dtype, device=x.device)
-        a = L.PvtArgs()
         a.dtype, a.out_dtype = ops.dtype_code(x.dtype), ops.dtype_code(y.dtype)
         a.B, a.N, a.C, a.H = B, N, C, self.num_heads
         a.Himg, a.Wimg, a.sr = int(H), int(W), self.sr_ratio
@@ -87,5 +80,82 @@ class Attention(StagedModule):
         a.kv_weight, a.kv_bias = ops._ptr(s["wkv"]), ops._ptr(s["bkv"])
         a.proj_weight, a.proj_bias = ops._ptr(s["wp"]), ops._ptr(s["bp"])
         a.sr_weight_t, a.sr_scale, a.sr_shift = ops._ptr(s["srw"]), ops._ptr(s["srs"]), ops._ptr(s["srb"])
+
+    def _check(self, x):
+        check_forward_mode(self, x, (self.attn_drop.p, self.proj_drop.p))
+        if self.sr_ratio > 1 and self.training:
+            raise NotImplementedError("train-mode BatchNorm (batch statistics) is not implemented: call .eval()")
+
+    def forward(self, x, H, W):
+        x, y_dtype = self._prepare_input(x)
+        self._check(x)
+        B, N, C = x.shape
+        x = x.contiguous()
+        s = self._staged(x.dtype)
+        y = torch.empty(B, N, C, dtype=self.out_dtype or y_dtype, device=x.device)
+        a = L.PvtArgs()
+        self._fill(a, x, y, H, W, s)
         ops.run_with_workspace(x, a, "pa_pvt_workspace_bytes", "pa_pvt_fwd")
         return y
+
+
+def block_attention_half(block, attn, norm1, x, H, W, rel_pos=None):
+    """``x + attn(norm1(x), H, W[, relative_pos])`` (pvt.py:106, segformer.py:76, cmt.py:131) as ONE C-ABI call
+    (``pa_pvt_block_attn_fwd``): LayerNorm kernel -> [reduction] -> q / [k|v] GEMMs -> attention core -> proj GEMM with the
+    residual x added in its epilogue.  The projections read the fp16 LayerNorm output, so their weights are staged as fp16."""
+    x, y_dtype = block._prepare_input(x)
+    attn._check(x)
+    check_forward_mode(block, x)
+    B, N, C = x.shape
+    x = x.contiguous()
+    s = attn._staged(torch.float16)
+    g, b = block._stage.get("ln", (norm1.weight, norm1.bias), lambda: (f32(norm1.weight), f32(norm1.bias)))
+    y = torch.empty(B, N, C, dtype=block.out_dtype or y_dtype, device=x.device)
+    a = L.PvtBlockArgs()
+    attn._fill(a.attn, x, y, H, W, s)
+    if rel_pos is not None:
+        a.attn.rel_pos = ops._ptr(attn._rel_pos(rel_pos, N))
+    a.ln_weight, a.ln_bias, a.ln_eps = ops._ptr(g), ops._ptr(b), float(norm1.eps)
+    ops.run_with_workspace(x, a, "pa_pvt_block_attn_workspace_bytes", "pa_pvt_block_attn_fwd")
+    return y
+
+
+class Mlp(nn.Module):
+    """pvt.py:13-31 (outside the attention hot path; kept so that Block is a complete drop-in)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, drop=0):
+        super().__init__()
+        hidden_features = hidden_features or in_features
+        out_features = out_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.gelu = nn.GELU()
+        self.drop1 = nn.Dropout(drop)
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop2 = nn.Dropout(drop)
+
+    def forward(self, x):
+        return self.drop2(self.fc2(self.drop1(self.gelu(self.fc1(x)))))
+
+
+class Block(StagedModule):
+    """Drop-in for ``pvt.Block`` (pvt.py:93-108): same constructor, sub-module names and ``state_dict`` keys (``norm1.*``,
+    ``attn.*``, ``norm2.*``, ``mlp.fc1/fc2.*``).  ``attention_half(x, H, W)`` = ``x + attn(norm1(x), H, W)`` (pvt.py:106) as one
+    C-ABI call; ``forward`` adds the MLP half (pvt.py:107) with the block's own PyTorch modules."""
+
+    def __init__(self, dim, num_heads=8, mlp_ratio=4, sr_ratio=1, qkv_bias=False, attn_drop=0, proj_drop=0):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = Attention(dim, num_heads, sr_ratio, qkv_bias, attn_drop, proj_drop)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio))
+        self.out_dtype = None
+        self._init_stage()
+
+    def attention_half(self, x, H, W):
+        return block_attention_half(self, self.attn, self.norm1, x, H, W)
+
+    def forward(self, x, H, W):
+        y = self.attention_half(x, H, W)
+        y = y.to(self.norm2.weight.dtype)
+        y = y + self.mlp(self.norm2(y))
+        return y.to(x.dtype)

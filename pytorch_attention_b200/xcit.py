@@ -1,4 +1,5 @@
-"""Drop-ins for ``vision_transformers/xcit.py``: ``XCA`` (xcit.py:233-265) and ``ClassAttention`` (xcit.py:159-188)."""
+"""Drop-ins for ``vision_transformers/xcit.py``: ``XCA`` (xcit.py:233-265), ``ClassAttention`` (xcit.py:159-188) and the attention
+half of ``XCABlock`` (xcit.py:291)."""
 from __future__ import annotations
 
 import torch
@@ -77,3 +78,57 @@ class ClassAttention(_XcitBase):
             y = y.to(y_dtype)
             y[:, 1:] = x_in[:, 1:]
         return y
+
+
+def xca_block_attention_half(attn: XCA, norm1: nn.LayerNorm, gamma1, x, out_dtype=None):
+    """``x + gamma1 * attn(norm1(x))`` (xcit.py:291, first line of ``XCABlock.forward``) as ONE C-ABI call
+    (``pa_xca_block_attn_fwd``): LayerNorm kernel -> qkv GEMM -> cross-covariance core -> proj GEMM with the residual in its
+    epilogue.  LayerScale is folded into the staged projection, ``gamma1[:,None] * proj.weight`` and ``gamma1 * proj.bias`` --
+    ``x + gamma1 * (O Wp^T + b) == x + O (gamma1 Wp)^T + gamma1 b``.  Usable on a reference ``XCABlock`` whose ``attn`` has been
+    swapped for this module's ``XCA``: ``xca_block_attention_half(blk.attn, blk.norm1, blk.gamma1, x)``."""
+    x, y_dtype = attn._prepare_input(x)
+    check_forward_mode(attn, x, (attn.attn_drop.p, attn.proj_drop.p))
+    for name, t in (("norm1.weight", norm1.weight), ("norm1.bias", norm1.bias), ("gamma1", gamma1)):
+        if t.device != x.device:
+            raise RuntimeError(f"'{name}' is on {t.device} but the input is on {x.device}")
+    x = x.contiguous()
+    B, N, C = x.shape
+    q, p = attn.qkv, attn.proj
+    wq, bq, wp, bp, g, b, temp = attn._stage.get(
+        "blk", (q.weight, q.bias, p.weight, p.bias, norm1.weight, norm1.bias, gamma1, attn.temperature),
+        lambda: (w16(q.weight, torch.float16), f32(q.bias),
+                 (gamma1.detach().float()[:, None] * p.weight.detach().float()).to(torch.float16).contiguous(),
+                 None if p.bias is None else (gamma1.detach().float() * p.bias.detach().float()).contiguous(),
+                 f32(norm1.weight), f32(norm1.bias), attn.temperature.detach().float().reshape(-1).contiguous()))
+    y = torch.empty(B, N, C, dtype=out_dtype or attn.out_dtype or y_dtype, device=x.device)
+    a = L.XcaBlockArgs()
+    a.attn.dtype, a.attn.out_dtype = ops.dtype_code(x.dtype), ops.dtype_code(y.dtype)
+    a.attn.B, a.attn.N, a.attn.C, a.attn.H = B, N, C, attn.num_heads
+    a.attn.x, a.attn.y = ops._ptr(x), ops._ptr(y)
+    a.attn.qkv_weight, a.attn.qkv_bias = ops._ptr(wq), ops._ptr(bq)
+    a.attn.proj_weight, a.attn.proj_bias = ops._ptr(wp), ops._ptr(bp)
+    a.attn.temperature = ops._ptr(temp)
+    a.ln_weight, a.ln_bias, a.ln_eps = ops._ptr(g), ops._ptr(b), float(norm1.eps)
+    ops.run_with_workspace(x, a, "pa_xca_block_attn_workspace_bytes", "pa_xca_block_attn_fwd")
+    return y
+
+
+class XCABlockAttentionHalf(StagedModule):
+    """The parameters of the first line of ``XCABlock.forward`` (xcit.py:291) under the reference block's own ``state_dict`` keys
+    (``norm1.*``, ``attn.*``, ``gamma1`` -- a subset of XCABlock's: ``load_state_dict(block.state_dict(), strict=False)``), and
+    ``forward(x) = x + gamma1 * attn(norm1(x))`` as one C-ABI call.  The LPI and MLP lines of the block (xcit.py:292-293) are not
+    on the attention path and stay with the reference's modules."""
+
+    def __init__(self, dim, num_heads, qkv_bias=False, qk_scale=None, attn_drop=0., drop=0., norm_layer=nn.LayerNorm, eta=None):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = XCA(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop)
+        self.gamma1 = nn.Parameter(eta * torch.ones(dim), requires_grad=True)
+        self.out_dtype = None
+        self._init_stage()
+
+    def attention_half(self, x):
+        return xca_block_attention_half(self.attn, self.norm1, self.gamma1, x, out_dtype=self.out_dtype)
+
+    def forward(self, x):
+        return self.attention_half(x)

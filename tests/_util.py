@@ -34,23 +34,39 @@ def rel_max(y, ref):
     return ((y - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
 
 
+def dropin_class(variant):
+    import pytorch_attention_b200 as pa
+    return {"vit": pa.vit.Attention, "vit_block": pa.vit.TransformerEncoder, "setr": pa.setr.Attention, "moat": pa.moat.Attention,
+            "pvt": pa.pvt.Attention, "pvt_block": pa.pvt.Block, "segformer": pa.segformer.Attention, "cmt": pa.cmt.Attention,
+            "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention, "cswin_block": pa.cswin.CSWinBlock, "xca": pa.xcit.XCA,
+            "xca_block": pa.xcit.XCABlockAttentionHalf, "class_attn": pa.xcit.ClassAttention}[variant]
+
+
 def build_dropin(spec, params, out_dtype=None):
     """Instantiate the B200 drop-in for a golden/oracle case spec and load the reference state_dict into it."""
-    import pytorch_attention_b200 as pa
-    cls = {"vit": pa.vit.Attention, "vit_block": pa.vit.TransformerEncoder, "setr": pa.setr.Attention, "moat": pa.moat.Attention, "pvt": pa.pvt.Attention, "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention,
-           "cswin_block": pa.cswin.CSWinBlock, "xca": pa.xcit.XCA, "class_attn": pa.xcit.ClassAttention}[spec["variant"]]
-    m = cls(**spec["ctor"]).eval()
-    m.load_state_dict(params)          # strict: keys and shapes must match the reference's
+    m = dropin_class(spec["variant"])(**spec["ctor"]).eval()
+    if spec.get("keep"):
+        # block cases store only the attention half's parameters: everything stored must load, nothing stored may be unknown,
+        # and what is missing must lie outside the stored prefixes (the block's MLP half)
+        res = m.load_state_dict(params, strict=False)
+        assert not res.unexpected_keys, res.unexpected_keys
+        assert not [k for k in res.missing_keys if k.startswith(tuple(spec["keep"]))], res.missing_keys
+    else:
+        m.load_state_dict(params)          # strict: keys and shapes must match the reference's
     if hasattr(m, "out_dtype"):
         m.out_dtype = out_dtype
     return m
 
 
-def run_dropin(spec, m, x):
+def run_dropin(spec, m, x, inputs=None):
     import torch
     with torch.no_grad():
-        if spec["variant"] == "pvt":
+        if spec["variant"] in ("pvt", "segformer"):
             return m(x, *spec["hw"])
-        if spec["variant"] in ("cswin_block", "vit_block"):
+        if spec["variant"] == "cmt":
+            return m(x, *spec["hw"], inputs["relative_pos"].float().to(x.device))
+        if spec["variant"] == "pvt_block":
+            return m.attention_half(x, *spec["hw"])
+        if spec["variant"] in ("cswin_block", "vit_block", "xca_block"):
             return m.attention_half(x)
         return m(x)

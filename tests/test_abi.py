@@ -7,6 +7,7 @@ import re
 import pytest
 
 from pytorch_attention_b200 import _lib as L
+from pytorch_attention_b200 import build
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -29,7 +30,7 @@ def test_header_symbols_exported_and_bound():
 
 def test_version_and_error_string():
     lib = L.load()
-    assert lib.pa_version() == 100
+    assert lib.pa_version() == build.header_version() == 101
     assert isinstance(lib.pa_last_error(), bytes)
 
 

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle.cases import GOLDEN_CASES, make_inputs, randomise_module_, run_oracle_case
-from _util import build_dropin, load_golden, rel_fro, rel_max, run_dropin
+from _util import build_dropin, dropin_class, load_golden, rel_fro, rel_max, run_dropin
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
@@ -15,7 +15,7 @@ def test_dropin_vs_reference_golden(name):
     spec = GOLDEN_CASES[name]
     inputs, params, y_ref = load_golden(name)
     m = build_dropin(spec, params).cuda()
-    y = run_dropin(spec, m, inputs["x"].half().cuda())
+    y = run_dropin(spec, m, inputs["x"].half().cuda(), inputs)
     assert y.shape == y_ref.shape
     yc = y.float().cpu()
     assert rel_fro(yc, y_ref) < TOL, rel_fro(yc, y_ref)
@@ -23,22 +23,21 @@ def test_dropin_vs_reference_golden(name):
 
 
 def _oracle_case(spec, seed=0, dtype=torch.float16):
-    """Fresh drop-in with randomised (fp16-representable) parameters; returns (module, x, oracle output)."""
+    """Fresh drop-in with randomised (fp16-representable) parameters; returns (module, x, oracle output).  Extra inputs of the
+    case (cmt's relative_pos) are left in ``spec["_inputs"]`` for run_dropin."""
     import pytorch_attention_b200 as pa  # noqa: F401
     torch.manual_seed(seed)
-    m = build_dropin(spec, _init_sd(spec))
+    m = build_dropin({k: v for k, v in spec.items() if k != "keep"}, _init_sd(spec))
     randomise_module_(m, seed + 11)
-    x = make_inputs(spec, seed)["x"]
+    inputs = make_inputs(spec, seed)
+    spec["_inputs"] = inputs
     params = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    ref = run_oracle_case(spec, {"x": x}, params)
-    return m.cuda(), x.to(dtype).cuda(), ref
+    ref = run_oracle_case(spec, inputs, params)
+    return m.cuda(), inputs["x"].to(dtype).cuda(), ref
 
 
 def _init_sd(spec):
-    import pytorch_attention_b200 as pa
-    cls = {"vit": pa.vit.Attention, "vit_block": pa.vit.TransformerEncoder, "setr": pa.setr.Attention, "moat": pa.moat.Attention, "pvt": pa.pvt.Attention, "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention,
-           "cswin_block": pa.cswin.CSWinBlock, "xca": pa.xcit.XCA, "class_attn": pa.xcit.ClassAttention}[spec["variant"]]
-    return cls(**spec["ctor"]).state_dict()
+    return dropin_class(spec["variant"])(**spec["ctor"]).state_dict()
 
 
 ORACLE_CASES = {
@@ -69,6 +68,24 @@ ORACLE_CASES = {
     # the zoo's own XCiT configuration (xcit_nano_12_p16, xcit.py:393: dim 128, 4 heads -> 32-wide heads, A is 32 x 32)
     "xca_nano_hd32": dict(variant="xca", ctor=dict(dim=128, num_heads=4), x=(3, 196, 128)),
     "classattn_nano_hd32": dict(variant="class_attn", ctor=dict(dim=128, num_heads=4), x=(3, 197, 128)),
+    # SegFormer mit_b0 stages (segformer.py:151-153: dims 32/64/160/256, heads 1/2/5/8 -> 32-wide heads, sr 8/4/2/1)
+    "segformer_b0_stage1": dict(variant="segformer", ctor=dict(dim=32, num_heads=1, sr_ratio=8), x=(1, 3136, 32), hw=(56, 56)),
+    "segformer_b0_stage2": dict(variant="segformer", ctor=dict(dim=64, num_heads=2, sr_ratio=4, qkv_bias=True), x=(2, 784, 64), hw=(28, 28)),
+    "segformer_b0_stage4": dict(variant="segformer", ctor=dict(dim=256, num_heads=8, sr_ratio=1), x=(2, 49, 256), hw=(7, 7)),
+    # 64-wide heads at a PVT-C3-like width, and a non-square token map
+    "segformer_512_sr8": dict(variant="segformer", ctor=dict(dim=512, num_heads=8, sr_ratio=8), x=(2, 4096, 512), hw=(64, 64)),
+    "segformer_nonsquare": dict(variant="segformer", ctor=dict(dim=128, num_heads=2, sr_ratio=2), x=(2, 12 * 20, 128), hw=(12, 20)),
+    # CMT cmt_s stages (cmt.py:225-228: dims 64/128/256/512, heads 1/2/4/8 -> 64-wide heads, sr 8/4/2/1: always 49 keys)
+    "cmt_s_stage1": dict(variant="cmt", ctor=dict(dim=64, num_heads=1, sr_ratio=8), x=(1, 3136, 64), hw=(56, 56)),
+    "cmt_s_stage3": dict(variant="cmt", ctor=dict(dim=256, num_heads=4, sr_ratio=2, qkv_bias=True), x=(2, 196, 256), hw=(14, 14)),
+    "cmt_s_stage4": dict(variant="cmt", ctor=dict(dim=512, num_heads=8, sr_ratio=1), x=(2, 49, 512), hw=(7, 7)),
+    # 240 keys after the reduction: the widest S tile of the single-slot kernel, both column halves carry the bias
+    "cmt_240keys": dict(variant="cmt", ctor=dict(dim=128, num_heads=2, sr_ratio=1), x=(1, 240, 128), hw=(12, 20)),
+    # block attention halves (row f-1): PVT C3 geometry, a dense-reduction block is covered through pvt.Block's entry point
+    "pvtblock_c3_b2": dict(variant="pvt_block", ctor=dict(dim=512, num_heads=8, sr_ratio=8), x=(2, 4096, 512), hw=(64, 64)),
+    "pvtblock_sr1_bias": dict(variant="pvt_block", ctor=dict(dim=128, num_heads=2, sr_ratio=1, qkv_bias=True), x=(2, 196, 128), hw=(14, 14)),
+    "xcablock_768": dict(variant="xca_block", ctor=dict(dim=768, num_heads=12, qkv_bias=True, eta=1.0), x=(2, 196, 768)),
+    "xcablock_nano_eta1e-5": dict(variant="xca_block", ctor=dict(dim=128, num_heads=4, eta=1e-5), x=(2, 196, 128)),
 }
 
 
@@ -76,7 +93,7 @@ ORACLE_CASES = {
 def test_dropin_vs_oracle(name):
     spec = ORACLE_CASES[name]
     m, x, ref = _oracle_case(spec, seed=len(name))
-    y = run_dropin(spec, m, x)
+    y = run_dropin(spec, m, x, spec["_inputs"])
     yc = y.float().cpu()
     assert rel_fro(yc, ref) < TOL, rel_fro(yc, ref)
     assert rel_max(yc, ref) < 2e-3, rel_max(yc, ref)

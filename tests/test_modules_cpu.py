@@ -133,3 +133,45 @@ def test_build_is_atomic_and_locked(tmp_path, monkeypatch):
     assert not list(tmp_path.glob("*.tmp.*"))
     b.build_lib()                       # fresh: no second compile
     assert len(calls) == 1
+
+
+def test_segformer_cmt_keys_and_defaults():
+    """segformer.Attention (segformer.py:18-31): q, fused kv, dense sr conv with bias; cmt.Attention (cmt.py:73-91): pvt's keys."""
+    m = pa.segformer.Attention(64, 2, qkv_bias=True, sr_ratio=4)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {
+        "q.weight": (64, 64), "q.bias": (64,), "kv.weight": (128, 64), "kv.bias": (128,), "sr.weight": (64, 64, 4, 4),
+        "sr.bias": (64,), "proj.weight": (64, 64), "proj.bias": (64,)}
+    assert "sr.weight" not in pa.segformer.Attention(64, 2).state_dict()       # sr_ratio=1: no reduction conv (segformer.py:26)
+    c = pa.cmt.Attention(128, 2, sr_ratio=2)
+    assert sorted(c.state_dict()) == sorted(pa.pvt.Attention(128, 2, sr_ratio=2).state_dict())
+    with pytest.raises(AssertionError):       # segformer.py:20 / cmt.py:76
+        pa.segformer.Attention(100, 3)
+    with pytest.raises(AssertionError):
+        pa.cmt.Attention(100, 3)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
+@pytest.mark.parametrize("modname,cls,kw", [
+    ("segformer", "Attention", dict(dim=64, num_heads=2, qkv_bias=True, sr_ratio=4)),
+    ("cmt", "Attention", dict(dim=128, num_heads=2, sr_ratio=2, qkv_bias=True)),
+    ("pvt", "Block", dict(dim=128, num_heads=2, sr_ratio=4)),
+])
+def test_siblings_match_live_reference_contract(modname, cls, kw):
+    ref = getattr(_ref(modname), cls)
+    ours = getattr(getattr(pa, modname), cls)
+    assert str(inspect.signature(ref.__init__)) == str(inspect.signature(ours.__init__))
+    if cls == "Attention":
+        assert str(inspect.signature(ref.forward)) == str(inspect.signature(ours.forward))
+    r, m = ref(**kw), ours(**kw)
+    assert {k: v.shape for k, v in r.state_dict().items()} == {k: v.shape for k, v in m.state_dict().items()}
+    m.load_state_dict(r.state_dict())          # reference weights load unchanged
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
+def test_xca_block_attention_half_loads_a_reference_block():
+    """XCABlockAttentionHalf holds the attention half's parameters under XCABlock's own keys (xcit.py:267-291)."""
+    blk = _ref("xcit").XCABlock(128, 4, qkv_bias=True, eta=1.0)
+    m = pa.xcit.XCABlockAttentionHalf(128, 4, qkv_bias=True, eta=1.0)
+    res = m.load_state_dict(blk.state_dict(), strict=False)
+    assert not res.missing_keys
+    assert all(k.split(".")[0] in ("norm2", "norm3", "mlp", "local_mp", "gamma2", "gamma3") for k in res.unexpected_keys)
