@@ -8,6 +8,7 @@
 #include "pa_misc.cuh"
 #include "pa_xca.cuh"
 #include "pa_attn_win.cuh"
+#include "pa_attn_proj.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -41,6 +42,7 @@ struct EnvCfg {
   int vit_cosched = -1;      // -1 unset (co-scheduled kernel when it qualifies), 0 never, 1 required
   int fused_bn1 = 0, fused_bn2 = 0;
   int cs_debug = 0, cs_lag = 0, gemm_one_set = 0, attn_two_slot = 0, cswin_two_kernels = 0;
+  int pvt_fused = 0;         // 1: attention core + proj GEMM as ONE kernel (pa_attn_proj.cuh; measured slower, see there)
 };
 std::atomic<const EnvCfg*> g_env{nullptr};
 std::mutex g_env_mu;
@@ -68,6 +70,7 @@ const EnvCfg* env_load() {
   c->gemm_one_set = getenv("PA_GEMM_ONE_SET") != nullptr;
   c->attn_two_slot = getenv("PA_ATTN_TWO_SLOT") != nullptr;
   c->cswin_two_kernels = getenv("PA_CSWIN_TWO_KERNELS") != nullptr;
+  c->pvt_fused = env_int("PA_PVT_FUSED", 0);
   return c;
 }
 inline const EnvCfg& env() {
@@ -530,6 +533,67 @@ int launch_attn_single_slot_t(const AttnPlan& plan, cudaStream_t st) {
 }
 int launch_attn_single_slot(const AttnPlan& plan, cudaStream_t st) {
   return plan.p.rel_pos ? launch_attn_single_slot_t<true>(plan, st) : launch_attn_single_slot_t<false>(plan, st);
+}
+
+// attention core + output projection in one kernel (pa_attn_proj.cuh): 64-wide heads, at most 64 keys, 128 <= C <= 512, 16-bit y
+inline bool attn_proj_ok(const AttnLaunch& a, int C, int y_dtype) {
+  return a.hd == 64 && !a.windowed && a.n_k <= 64 && C == a.H * 64 && C >= 128 && C <= 512 && y_dtype != PA_DTYPE_F32 &&
+         a.rel_pos == nullptr && !a.add_into_out;
+}
+int launch_attn_proj(const AttnLaunch& a, const void* wp, const float* bias, void* y, int y_dtype, cudaStream_t st) {
+  int rc;
+  const int C = a.H * 64;
+  AttnProjParams p = {};
+  p.G = a.G; p.H = a.H; p.n_q = a.n_q; p.n_k = a.n_k; p.kb = (a.n_k + 15) / 16 * 16;
+  p.q_tiles = (a.n_q + 127) / 128; p.units = a.G * p.q_tiles; p.C = C;
+  p.q_col0 = a.q_col0; p.k_col0 = a.k_col0; p.v_col0 = a.v_col0;
+  p.scale_log2e = a.scale * 1.4426950408889634f;
+  p.bias = bias; p.out_dtype = y_dtype;
+  p.idesc_s = make_idesc(128, p.kb, PA_F16, PA_F16, 0, 0);
+  p.idesc_o = make_idesc(128, 64, PA_F16, PA_F16, 0, 1);
+  p.idesc_y = make_idesc(128, 128, PA_F16, PA_F16, 0, 0);
+  p.trace = g_gemm_trace;
+  CUtensorMap tq, tk, tv, tw, ty;
+  {
+    uint64_t dims[3] = {(uint64_t)a.ldq, (uint64_t)a.n_q, (uint64_t)a.G};
+    uint64_t str[2] = {(uint64_t)a.ldq * 2, (uint64_t)a.q_group * 2};
+    uint32_t box[3] = {64, 128, 1};
+    if ((rc = make_tmap_16b(&tq, PA_DTYPE_F16, a.q, 3, dims, str, box, TM_SWZ_128))) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)a.ldk, (uint64_t)a.n_k, (uint64_t)a.G};
+    uint64_t str[2] = {(uint64_t)a.ldk * 2, (uint64_t)a.k_group * 2};
+    uint32_t box[3] = {64, (uint32_t)p.kb, 1};
+    if ((rc = make_tmap_16b(&tk, PA_DTYPE_F16, a.k, 3, dims, str, box, TM_SWZ_128))) return rc;
+    if ((rc = make_tmap_16b(&tv, PA_DTYPE_F16, a.v, 3, dims, str, box, TM_SWZ_128))) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)C, (uint64_t)C, 1};
+    uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)C * C * 2};
+    uint32_t box[3] = {64, 64, 1};             // half of a [128 n x 64 k] tile: each CTA of a pair fetches one and multicasts it
+    if ((rc = make_tmap_16b(&tw, PA_DTYPE_F16, wp, 3, dims, str, box, TM_SWZ_128))) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)C, (uint64_t)a.n_q, (uint64_t)a.G};
+    uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)a.n_q * C * 2};
+    uint32_t box[3] = {32, 32, 1};
+    if ((rc = make_tmap_16b(&ty, y_dtype, y, 3, dims, str, box, TM_SWZ_64))) return rc;
+  }
+  static SmemAttr smem_attr;
+  if ((rc = smem_attr.ensure(attn_proj_kernel, AP_SMEM_BYTES))) return rc;
+  const int max_pairs = num_sms() / 2, want_pairs = (p.units + 1) / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (want_pairs < max_pairs ? want_pairs : max_pairs));
+  cfg.blockDim = dim3(AP_THREADS);
+  cfg.dynamicSmemBytes = AP_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  PA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_proj_kernel, tq, tk, tv, tw, ty, p));
+  launch_counter()++;
+  return PA_OK;
 }
 
 int attn_impl(const pa_attn_args* a, cudaStream_t st) {
@@ -1102,6 +1166,11 @@ static int pvt_run(const pa_pvt_args* a, const void* x_in, int x_dtype, const vo
   at.o = ob; at.ldo = C; at.o_group = (long long)a->N * C; at.o_col0 = 0;
   at.scale = a->scale;
   at.rel_pos = a->rel_pos;                  // cmt.py:100
+  // opt-in (PA_PVT_FUSED=1; correct, but measured slower than the two launches: pa_attn_proj.cuh): attention core and
+  // projection in ONE kernel for the few-key stages of PVT / SegFormer -- O stays in TMEM
+  if (env().pvt_fused && residual == nullptr && attn_proj_ok(at, C, a->out_dtype)) {
+    if ((reinterpret_cast<uintptr_t>(a->y) & 15) == 0) return launch_attn_proj(at, a->proj_weight, a->proj_bias, a->y, a->out_dtype, st);
+  }
   if ((rc = attn_launch(at, st))) return rc;
   return linear(ob, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st,
                 residual, C, a->dtype);

@@ -216,3 +216,29 @@ def test_c5_vit_l_shard_all_images_vs_oracle():
         y = m.cuda()(x.cuda()).float().cpu()
     per_image = ((y - ref).flatten(1).norm(dim=1) / ref.flatten(1).norm(dim=1))
     assert per_image.max().item() < TOL, per_image.max().item()
+
+
+@pytest.mark.parametrize("name", ["pvt_c3_b2", "pvt_t_stage3", "pvt_t_stage4", "segformer_512_sr8", "segformer_nonsquare"])
+def test_opt_in_fused_attention_projection_kernel(name, monkeypatch):
+    """PA_PVT_FUSED=1: attention core + output projection in one kernel (pa_attn_proj.cuh; O stays in TMEM as the projection's
+    A operand).  Not the default (measured slower) but kept correct: same oracle, same tolerance, one launch fewer."""
+    from pytorch_attention_b200 import _lib
+    spec = ORACLE_CASES[name]
+    m, x, ref = _oracle_case(spec, seed=len(name))
+    n0 = _lib.launch_count()
+    y_sep = run_dropin(spec, m, x, spec["_inputs"])
+    n_sep = _lib.launch_count() - n0
+    monkeypatch.setenv("PA_PVT_FUSED", "1")
+    _lib.reload_env()
+    try:
+        n0 = _lib.launch_count()
+        y = run_dropin(spec, m, x, spec["_inputs"])
+        n_fused = _lib.launch_count() - n0
+    finally:
+        monkeypatch.delenv("PA_PVT_FUSED")
+        _lib.reload_env()
+    assert n_fused == n_sep - 1
+    yc = y.float().cpu()
+    assert rel_fro(yc, ref) < TOL, rel_fro(yc, ref)
+    assert rel_max(yc, ref) < 2e-3, rel_max(yc, ref)
+    assert rel_fro(yc, y_sep.float().cpu()) < TOL
