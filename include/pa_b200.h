@@ -139,6 +139,26 @@ typedef struct {
 size_t pa_vit_block_attn_workspace_bytes(const pa_vit_block_args* a);
 int pa_vit_block_attn_fwd(const pa_vit_block_args* a, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------- bvit.Broad_Attention  (bvit.py:49-76) */
+/* ViT's math with an inner width heads * dim_head that need not equal dim, no qkv bias, and q, k, v handed back to the caller
+ * (BViT's parameter-free broad attention reads them from every layer, bvit.py:88-98): the qkv projection is written to a
+ * caller-owned buffer instead of the workspace and forward() returns views of it.  Launches: GEMM(qkv) -> attention core ->
+ * GEMM(out); without an output projection (heads == 1 and dim_head == dim: nn.Identity, bvit.py:52, 61-64) the attention core
+ * writes y directly. */
+typedef struct {
+  int dtype, out_dtype;      /* out_dtype must be fp16 when out_weight is NULL */
+  int B, N, C, H, dim_head;  /* inner = H * dim_head; dim_head a multiple of 16 from 32 to 192 */
+  float scale;               /* dim_head ** -0.5 (bvit.py:55) */
+  const void* x;             /* [B,N,C] */
+  const void* qkv_weight;    /* [3*inner, C] (dtype): to_qkv.weight, rows ordered (q|k|v, head, d) (bvit.py:67-68) */
+  const void* out_weight;    /* [C, inner] fp16: to_out.0.weight, or NULL (Identity) */
+  const float* out_bias;     /* [C] or NULL */
+  void* qkv;                 /* OUT [B,N,3*inner] fp16 */
+  void* y;                   /* OUT [B,N,C] (Identity: [B,N,inner] with inner == C) */
+} pa_bvit_args;
+size_t pa_bvit_workspace_bytes(const pa_bvit_args* a);
+int pa_bvit_fwd(const pa_bvit_args* a, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- pvt.Attention  (pvt.py:52-91) */
 typedef struct {
   int dtype, out_dtype;

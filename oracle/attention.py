@@ -62,6 +62,20 @@ def vit_attention(x, qkv_weight, qkv_bias, proj_weight, proj_bias, num_heads, sc
     return _lin(o, proj_weight, proj_bias)                      # ViT.py:87
 
 
+def bvit_broad_attention(x, to_qkv_weight, to_out_weight, to_out_bias, heads, dim_head):
+    """bvit.Broad_Attention.forward (bvit.py:66-76): returns (out, q, k, v) with q, k, v as [B, heads, N, dim_head].
+    Inner width heads * dim_head; to_qkv has no bias; without an output projection (to_out = Identity, bvit.py:52) out is the
+    concatenated heads."""
+    B, N, _ = x.shape
+    qkv = _lin(x, to_qkv_weight).reshape(B, N, 3, heads, dim_head)          # chunk(3) + 'b n (h d) -> b h n d'
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    s = torch.einsum("bhnd,bhmd->bhnm", q, k) * dim_head ** -0.5
+    p = _softmax_last(s)
+    o = torch.einsum("bhnm,bhmd->bnhd", p, v).reshape(B, N, heads * dim_head)
+    out = o if to_out_weight is None else _lin(o, to_out_weight, to_out_bias)
+    return out, q, k, v
+
+
 def vit_block_attention_half(x, ln_weight, ln_bias, qkv_weight, qkv_bias, proj_weight, proj_bias, num_heads, eps=1e-5):
     """First half of ViT.TransformerEncoder.forward (ViT.py:116): x + attn(layernorm1(x)).  LayerNorm over the channel axis,
     biased variance, eps inside the square root (nn.LayerNorm)."""

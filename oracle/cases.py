@@ -23,6 +23,9 @@ GOLDEN_CASES = {
     # setr.Attention(dim, num_heads=8) setr.py:50-72 and moat.Attention(dim, num_heads=8) moat.py:62-84: ViT's math
     "setr_b2_n100_c256_default_heads": dict(variant="setr", ctor=dict(dim=256), x=(2, 100, 256)),
     "moat_b2_n196_c512_default_heads_bias": dict(variant="moat", ctor=dict(dim=512, qkv_bias=True), x=(2, 196, 512)),
+    # bvit.Broad_Attention(dim, heads, dim_head): inner width != dim, (out, q, k, v) returned     bvit.py:49-76
+    "bvit_b2_n65_c192_h3_hd64": dict(variant="bvit", ctor=dict(dim=192, heads=3, dim_head=64), x=(2, 65, 192)),
+    "bvit_b2_n50_c96_h4_hd32": dict(variant="bvit", ctor=dict(dim=96, heads=4, dim_head=32), x=(2, 50, 96)),
     # pvt.Attention(dim, num_heads, sr_ratio)            pvt.py:52-91
     "pvt_b2_16x16_c128_h2_sr4": dict(variant="pvt", ctor=dict(dim=128, num_heads=2, sr_ratio=4), x=(2, 256, 128), hw=(16, 16)),
     "pvt_b2_8x8_c128_h2_sr1_bias": dict(variant="pvt", ctor=dict(dim=128, num_heads=2, sr_ratio=1, qkv_bias=True), x=(2, 64, 128), hw=(8, 8)),
@@ -58,6 +61,7 @@ _REF_CLASS = {
     "vit_block": ("ViT", "TransformerEncoder"),
     "setr": ("setr", "Attention"),
     "moat": ("moat", "Attention"),
+    "bvit": ("bvit", "Broad_Attention"),
     "pvt": ("pvt", "Attention"),
     "pvt_block": ("pvt", "Block"),
     "segformer": ("segformer", "Attention"),
@@ -123,7 +127,7 @@ def make_inputs(spec, seed=0):
 def load_reference(ref_path):
     if ref_path not in sys.path:
         sys.path.insert(0, ref_path)
-    return {m: importlib.import_module(m) for m in ("ViT", "pvt", "cvt", "cswin", "xcit", "moat", "segformer", "cmt")}
+    return {m: importlib.import_module(m) for m in ("ViT", "pvt", "cvt", "cswin", "xcit", "moat", "segformer", "cmt", "bvit")}
 
 
 def load_reference_class(ref_path, module, cls):
@@ -152,6 +156,8 @@ def reference_forward(spec, mod, x, inputs=None):
         if v == "pvt_block":
             # attention half only (pvt.py:106), with the reference block's own sub-modules
             return x + mod.attn(mod.norm1(x), *spec["hw"])
+        if v == "bvit":
+            return mod(x)[0]           # (out, q, k, v): the golden file pins out; q/k/v are checked in tests/test_oracle_vs_reference.py
         if v == "xca_block":
             # first line of XCABlock.forward (xcit.py:291)
             return x + mod.gamma1 * mod.attn(mod.norm1(x))
@@ -214,6 +220,9 @@ def run_oracle_case(spec, inputs, params, dtype=torch.float32):
                  "sr.0.weight", "sr.0.bias", "sr.1.weight", "sr.1.bias", "sr.1.running_mean", "sr.1.running_var")
         return A.pvt_attention(x, spec["hw"][0], spec["hw"][1], num_heads=c["num_heads"],
                                sr_ratio=c.get("sr_ratio", 1), **kw)
+    if v == "bvit":
+        return A.bvit_broad_attention(x, P["to_qkv.weight"], P.get("to_out.0.weight"), P.get("to_out.0.bias"),
+                                      c.get("heads", 8), c.get("dim_head", 64))[0]
     if v == "pvt_block":
         keys = ("q.weight", "q.bias", "k.weight", "k.bias", "v.weight", "v.bias", "proj.weight", "proj.bias",
                 "sr.0.weight", "sr.0.bias", "sr.1.weight", "sr.1.bias", "sr.1.running_mean", "sr.1.running_var")

@@ -44,6 +44,11 @@ class VitBlockArgs(C.Structure):
     _fields_ = [("attn", VitArgs), ("ln_weight", _vp), ("ln_bias", _vp), ("ln_eps", _f)]
 
 
+class BvitArgs(C.Structure):
+    _fields_ = [("dtype", _i), ("out_dtype", _i), ("B", _i), ("N", _i), ("C", _i), ("H", _i), ("dim_head", _i), ("scale", _f),
+                ("x", _vp), ("qkv_weight", _vp), ("out_weight", _vp), ("out_bias", _vp), ("qkv", _vp), ("y", _vp)]
+
+
 class PvtArgs(C.Structure):
     _fields_ = [("dtype", _i), ("out_dtype", _i), ("B", _i), ("N", _i), ("C", _i), ("H", _i),
                 ("Himg", _i), ("Wimg", _i), ("sr", _i), ("scale", _f),
@@ -108,6 +113,8 @@ SYMBOLS = {
     "pa_vit_fwd": (_i, [C.POINTER(VitArgs), _vp, C.c_size_t, _vp]),
     "pa_vit_block_attn_workspace_bytes": (C.c_size_t, [C.POINTER(VitBlockArgs)]),
     "pa_vit_block_attn_fwd": (_i, [C.POINTER(VitBlockArgs), _vp, C.c_size_t, _vp]),
+    "pa_bvit_workspace_bytes": (C.c_size_t, [C.POINTER(BvitArgs)]),
+    "pa_bvit_fwd": (_i, [C.POINTER(BvitArgs), _vp, C.c_size_t, _vp]),
     "pa_pvt_workspace_bytes": (C.c_size_t, [C.POINTER(PvtArgs)]),
     "pa_pvt_fwd": (_i, [C.POINTER(PvtArgs), _vp, C.c_size_t, _vp]),
     "pa_pvt_block_attn_workspace_bytes": (C.c_size_t, [C.POINTER(PvtBlockArgs)]),

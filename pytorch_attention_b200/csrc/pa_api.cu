@@ -1087,6 +1087,48 @@ void pa_reload_env(void) {
   g_env.store(env_load(), std::memory_order_release);
 }
 
+// ================================================================ BViT  (bvit.py:49-76)
+static int bvit_check(const pa_bvit_args* a) {
+  if (!a) return fail(PA_ERR_NULL, "pa_bvit: args is NULL");
+  if (a->B <= 0 || a->N <= 0 || a->C <= 0 || a->H <= 0 || a->dim_head <= 0) return fail(PA_ERR_BAD_SHAPE, "pa_bvit: B,N,C,H,dim_head must be positive");
+  if (!attn_hd_ok(a->dim_head)) return fail(PA_ERR_UNSUPPORTED, "pa_bvit: dim_head %d unsupported (multiples of 16 from 32 to 192)", a->dim_head);
+  if (a->C % 8) return fail(PA_ERR_BAD_SHAPE, "pa_bvit: dim must be a multiple of 8");
+  if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "pa_bvit: dtype must be fp16/bf16");
+  if (!a->out_weight && (a->H * a->dim_head != a->C || a->out_dtype != PA_DTYPE_F16))
+    return fail(PA_ERR_UNSUPPORTED, "pa_bvit: without an output projection the inner width must equal dim and y must be fp16");
+  return PA_OK;
+}
+
+size_t pa_bvit_workspace_bytes(const pa_bvit_args* a) {
+  if (bvit_check(a)) return 0;
+  return align_up((size_t)a->B * a->N * a->H * a->dim_head * 2, 1024) + 1024;
+}
+
+int pa_bvit_fwd(const pa_bvit_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = bvit_check(a);
+  if (rc) return rc;
+  if (!a->x || !a->qkv_weight || !a->qkv || !a->y) return fail(PA_ERR_NULL, "pa_bvit_fwd: x/qkv_weight/qkv/y must be non-NULL");
+  const size_t need = pa_bvit_workspace_bytes(a);
+  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_bvit_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+  if ((rc = current_device_check())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = a->C, inner = a->H * a->dim_head;
+  const long long rows = (long long)a->B * a->N;
+  Arena ws(workspace);
+  void* obuf = a->out_weight ? ws.take((size_t)rows * inner * 2) : a->y;
+  // qkv = x Wqkv^T, columns (q|k|v, head, d)          (bvit.py:67-68)
+  if ((rc = linear(a->x, a->dtype, C, a->qkv_weight, a->dtype, nullptr, a->qkv, PA_DTYPE_F16, 3 * inner, rows, 3 * inner, C, st))) return rc;
+  AttnLaunch at = {};
+  at.hd = a->dim_head; at.G = a->B; at.H = a->H; at.n_q = a->N; at.n_k = a->N;
+  at.q = a->qkv; at.ldq = 3 * inner; at.q_group = (long long)a->N * 3 * inner; at.q_col0 = 0;
+  at.k = a->qkv; at.v = a->qkv; at.ldk = 3 * inner; at.k_group = (long long)a->N * 3 * inner; at.k_col0 = inner; at.v_col0 = 2 * inner;
+  at.o = obuf; at.ldo = inner; at.o_group = (long long)a->N * inner; at.o_col0 = 0;
+  at.scale = a->scale;
+  if ((rc = attn_launch(at, st))) return rc;           // bvit.py:70-75
+  if (!a->out_weight) return PA_OK;
+  return linear(obuf, PA_DTYPE_F16, inner, a->out_weight, PA_DTYPE_F16, a->out_bias, a->y, a->out_dtype, C, rows, C, inner, st);
+}
+
 // ================================================================ PVT  (pvt.py:52-91)
 static int pvt_check(const pa_pvt_args* a) {
   if (!a) return fail(PA_ERR_NULL, "pa_pvt: args is NULL");

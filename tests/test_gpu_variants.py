@@ -242,3 +242,27 @@ def test_opt_in_fused_attention_projection_kernel(name, monkeypatch):
     assert rel_fro(yc, ref) < TOL, rel_fro(yc, ref)
     assert rel_max(yc, ref) < 2e-3, rel_max(yc, ref)
     assert rel_fro(yc, y_sep.float().cpu()) < TOL
+
+
+@pytest.mark.parametrize("ctor,n", [(dict(dim=192, heads=3, dim_head=64), 197), (dict(dim=64, heads=1, dim_head=64), 100),
+                                    (dict(dim=256, heads=2, dim_head=96), 65)])
+def test_bvit_returns_out_q_k_v(ctor, n):
+    """bvit.Broad_Attention.forward returns (out, q, k, v) (bvit.py:76): all four against the oracle, including the
+    no-projection case (heads == 1 and dim_head == dim, bvit.py:52) and an inner width != dim with 96-wide heads."""
+    import pytorch_attention_b200 as pa
+    from oracle import attention as A
+    from oracle.cases import round_fp16_
+    torch.manual_seed(n)
+    m = pa.bvit.Broad_Attention(**ctor).eval()
+    with torch.no_grad():
+        for p in m.parameters():
+            round_fp16_(p)
+    x = round_fp16_(torch.randn(2, n, ctor["dim"]))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ref = A.bvit_broad_attention(x, sd["to_qkv.weight"], sd.get("to_out.0.weight"), sd.get("to_out.0.bias"), ctor["heads"], ctor["dim_head"])
+    with torch.no_grad():
+        got = m.cuda()(x.half().cuda())
+    assert len(got) == 4
+    for g, r in zip(got, ref):
+        assert g.shape == r.shape
+        assert rel_fro(g.float().cpu(), r) < TOL

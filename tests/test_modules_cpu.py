@@ -175,3 +175,14 @@ def test_xca_block_attention_half_loads_a_reference_block():
     res = m.load_state_dict(blk.state_dict(), strict=False)
     assert not res.missing_keys
     assert all(k.split(".")[0] in ("norm2", "norm3", "mlp", "local_mp", "gamma2", "gamma3") for k in res.unexpected_keys)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
+@pytest.mark.parametrize("kw", [dict(dim=192, heads=3, dim_head=64), dict(dim=64, heads=1, dim_head=64)])
+def test_bvit_broad_attention_matches_live_reference_contract(kw):
+    ref = _ref("bvit").Broad_Attention
+    assert str(inspect.signature(ref.__init__)) == str(inspect.signature(pa.bvit.Broad_Attention.__init__))
+    r, m = ref(**kw), pa.bvit.Broad_Attention(**kw)
+    assert {k: v.shape for k, v in r.state_dict().items()} == {k: v.shape for k, v in m.state_dict().items()}
+    m.load_state_dict(r.state_dict())
+    assert isinstance(m.to_out, torch.nn.Identity) == isinstance(r.to_out, torch.nn.Identity)

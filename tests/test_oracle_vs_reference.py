@@ -51,3 +51,24 @@ def test_oracle_vs_live_reference_extra_configs(name):
     y = run_oracle_case(spec, case["inputs"], case["params"])
     tol = 5e-6 * max(1.0, case["y_ref"].abs().max().item())
     assert (y - case["y_ref"]).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("ctor", [dict(dim=192, heads=3, dim_head=64), dict(dim=64, heads=1, dim_head=64)])
+def test_bvit_q_k_v_and_identity_projection_vs_live_reference(ctor):
+    """Broad_Attention returns (out, q, k, v) (bvit.py:76); with heads == 1 and dim_head == dim there is no output projection
+    (bvit.py:52, 61-64).  All four outputs of the restatement against the live module."""
+    from oracle import attention as A
+    from oracle.cases import round_fp16_
+    ref_cls = load_reference(REF)["bvit"].Broad_Attention
+    torch.manual_seed(3)
+    mod = ref_cls(**ctor).eval()
+    with torch.no_grad():
+        for p in mod.parameters():
+            round_fp16_(p)
+        x = round_fp16_(torch.randn(2, 37, ctor["dim"]))
+        ref = mod(x)
+    sd = mod.state_dict()
+    got = A.bvit_broad_attention(x, sd["to_qkv.weight"], sd.get("to_out.0.weight"), sd.get("to_out.0.bias"), ctor["heads"], ctor["dim_head"])
+    for r, g in zip(ref, got):
+        assert r.shape == g.shape
+        assert (r - g).abs().max().item() <= 5e-6 * max(1.0, r.abs().max().item())
