@@ -216,6 +216,9 @@ typedef struct {
   const void* proj_weight;   /* [C,C] fp16 (proj.weight, 1x1) */
   const float* proj_bias;    /* [C] */
   void* y;                   /* [B,C,Himg,Wimg] */
+  const void* residual;      /* NULL, or an NCHW tensor (dtype) added to the projection's result in its epilogue.  With ks = 1,
+                                a unit depthwise tap, H = 1, scale = 1 and proj_weight = alpha * I this entry point is
+                                dual_attention.PAM (attention_mechanisms/dual_attention.py:12-28): out = alpha * attn(x) + x */
 } pa_cvt_args;
 size_t pa_cvt_workspace_bytes(const pa_cvt_args* a);
 int pa_cvt_fwd(const pa_cvt_args* a, void* workspace, size_t workspace_bytes, void* stream);

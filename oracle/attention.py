@@ -358,3 +358,19 @@ def xca_block_attention_half(x, norm1_weight, norm1_bias, gamma1, qkv_weight, qk
     norm_layer = partial(nn.LayerNorm, eps=1e-6); a bare XCABlock uses nn.LayerNorm's 1e-5 -- the caller passes the module's."""
     h = _layer_norm_rows(x, norm1_weight, norm1_bias, eps)
     return x + gamma1 * xca_attention(h, qkv_weight, qkv_bias, proj_weight, proj_bias, temperature, num_heads)
+
+
+# --------------------------------------------------------------------------
+# DANet position attention module (reference: attention_mechanisms/dual_attention.py:12-28)
+# --------------------------------------------------------------------------
+def pam_attention(x, b_weight, b_bias, c_weight, c_bias, d_weight, d_bias, alpha):
+    """PAM.forward (dual_attention.py:21-28): NCHW in and out, one head as wide as the channel count, no score scale:
+    attn[i, j] = softmax_j( b(x)[:, i] . c(x)[:, j] ),  y[:, i] = sum_j attn[i, j] d(x)[:, j],  out = alpha * y + x."""
+    n, c, h, w = x.shape
+    t = x.reshape(n, c, h * w)
+    def conv(wt, bs):
+        return torch.einsum("oc,bcn->bon", wt.reshape(c, c), t) + bs[None, :, None]
+    B_, C_, D_ = conv(b_weight, b_bias), conv(c_weight, c_bias), conv(d_weight, d_bias)
+    p = _softmax_last(torch.einsum("bci,bcj->bij", B_, C_))
+    y = torch.einsum("bij,bcj->bci", p, D_).reshape(n, c, h, w)
+    return alpha * y + x

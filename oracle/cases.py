@@ -51,6 +51,9 @@ GOLDEN_CASES = {
     # xcit.XCA / xcit.ClassAttention                       xcit.py:233-265, 159-188
     "xca_b2_n196_c128_h2": dict(variant="xca", ctor=dict(dim=128, num_heads=2, qkv_bias=True), x=(2, 196, 128)),
     "classattn_b2_n197_c128_h2": dict(variant="class_attn", ctor=dict(dim=128, num_heads=2, qkv_bias=True), x=(2, 197, 128)),
+    # dual_attention.PAM(dim): NCHW, one head as wide as the channel count, no scale, alpha * y + x   dual_attention.py:12-28
+    "pam_b2_c64_16x16": dict(variant="pam", ctor=dict(dim=64), x=(2, 64, 16, 16)),
+    "pam_b2_c96_12x20": dict(variant="pam", ctor=dict(dim=96), x=(2, 96, 12, 20)),
     # xcit.XCABlock, attention half: x + gamma1 * attn(norm1(x))          xcit.py:267-291
     "xcablock_b2_n196_c128_h2": dict(variant="xca_block", ctor=dict(dim=128, num_heads=2, qkv_bias=True, eta=1.0), x=(2, 196, 128),
                                      keep=("norm1.", "attn.", "gamma1")),
@@ -67,6 +70,7 @@ _REF_CLASS = {
     "segformer": ("segformer", "Attention"),
     "cmt": ("cmt", "Attention"),
     "xca_block": ("xcit", "XCABlock"),
+    "pam": ("dual_attention", "PAM"),
     "cvt": ("cvt", "Attention"),
     "lepe": ("cswin", "LePEAttention"),
     "cswin_block": ("cswin", "CSWinBlock"),
@@ -99,6 +103,8 @@ def randomise_module_(mod, seed):
         for name, p in mod.named_parameters():
             if name.endswith("temperature"):
                 p.copy_(torch.rand(p.shape, generator=g) * 1.5 + 0.5)
+            if name.endswith("alpha"):
+                p.copy_(torch.rand(p.shape, generator=g) + 0.5)       # PAM: alpha = 0 at init would hide the whole attention term
             if name.endswith("gamma1"):
                 p.copy_((torch.rand(p.shape, generator=g) + 0.5) * p)   # LayerScale (xcit.py:285) = eta * ones: spread it so a dropped gamma shows
             if name.endswith(".bias") and "norm" not in name and "sr.1" not in name and "qkv.1" not in name:
@@ -134,6 +140,12 @@ def load_reference_class(ref_path, module, cls):
     """The reference class object.  ``setr.py`` builds and runs a whole SETR model at import time (setr.py:131-134), so for
     that file only the module's imports and its own class definitions are executed -- still the reference's code, read
     from where it lies, just without the module-level demo."""
+    if module == "dual_attention":           # the one class outside vision_transformers/: attention_mechanisms/dual_attention.py
+        import os
+        am = os.path.join(os.path.dirname(os.path.abspath(ref_path)), "attention_mechanisms")
+        if am not in sys.path:
+            sys.path.insert(0, am)
+        return getattr(importlib.import_module(module), cls)
     if module != "setr":
         return getattr(load_reference(ref_path)[module], cls)
     import ast
@@ -220,6 +232,8 @@ def run_oracle_case(spec, inputs, params, dtype=torch.float32):
                  "sr.0.weight", "sr.0.bias", "sr.1.weight", "sr.1.bias", "sr.1.running_mean", "sr.1.running_var")
         return A.pvt_attention(x, spec["hw"][0], spec["hw"][1], num_heads=c["num_heads"],
                                sr_ratio=c.get("sr_ratio", 1), **kw)
+    if v == "pam":
+        return A.pam_attention(x, P["b.weight"], P["b.bias"], P["c.weight"], P["c.bias"], P["d.weight"], P["d.bias"], P["alpha"])
     if v == "bvit":
         return A.bvit_broad_attention(x, P["to_qkv.weight"], P.get("to_out.0.weight"), P.get("to_out.0.bias"),
                                       c.get("heads", 8), c.get("dim_head", 64))[0]

@@ -66,7 +66,7 @@ class CvtArgs(C.Structure):
     _fields_ = [("dtype", _i), ("out_dtype", _i), ("B", _i), ("C", _i), ("H", _i), ("Himg", _i), ("Wimg", _i), ("ks", _i),
                 ("scale", _f),
                 ("x", _vp), ("dw_weight", _vp), ("dw_scale", _vp), ("dw_shift", _vp), ("qkv_weight", _vp), ("qkv_bias", _vp),
-                ("proj_weight", _vp), ("proj_bias", _vp), ("y", _vp)]
+                ("proj_weight", _vp), ("proj_bias", _vp), ("y", _vp), ("residual", _vp)]
 
 
 class XcitArgs(C.Structure):

@@ -611,6 +611,16 @@ int attn_impl(const pa_attn_args* a, cudaStream_t st) {
   return attn_launch(l, st);
 }
 
+// LayerNorm row kernel: the instantiation that holds exactly the row's width in registers (C <= 1024), else the generic kernel
+void launch_layernorm(const LnParams& ln, cudaStream_t st) {
+  const int blocks = (int)((ln.rows * 32 + 255) / 256);
+  if (ln.C % 8 == 0 && ln.C <= 256) layernorm_rows_kernel<1><<<blocks, 256, 0, st>>>(ln);
+  else if (ln.C % 8 == 0 && ln.C <= 512) layernorm_rows_kernel<2><<<blocks, 256, 0, st>>>(ln);
+  else if (ln.C % 8 == 0 && ln.C <= 768) layernorm_rows_kernel<3><<<blocks, 256, 0, st>>>(ln);
+  else if (ln.C % 8 == 0 && ln.C <= 1024) layernorm_rows_kernel<4><<<blocks, 256, 0, st>>>(ln);
+  else layernorm_kernel<<<blocks, 256, 0, st>>>(ln);
+}
+
 int grid_for(long long work_items, int threads) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -1049,7 +1059,7 @@ int pa_vit_block_attn_fwd(const pa_vit_block_args* b, void* workspace, size_t wo
   // img = layernorm1(x)   (ViT.py:116), fp16
   LnParams ln;
   ln.x = a->x; ln.out = img; ln.gamma = b->ln_weight; ln.beta = b->ln_bias; ln.rows = rows; ln.C = C; ln.dtype = a->dtype; ln.eps = b->ln_eps;
-  layernorm_kernel<<<(int)((rows * 32 + 255) / 256), 256, 0, st>>>(ln);
+  launch_layernorm(ln, st);
   PA_CUDA_OK(cudaGetLastError());
   launch_counter()++;
   // x + proj(attention(img)): the residual rides in the proj GEMM's epilogue
@@ -1259,7 +1269,7 @@ int pa_pvt_block_attn_fwd(const pa_pvt_block_args* b, void* workspace, size_t wo
   // img = norm1(x)   (pvt.py:106, segformer.py:76, cmt.py:131), fp16
   LnParams ln;
   ln.x = a->x; ln.out = img; ln.gamma = b->ln_weight; ln.beta = b->ln_bias; ln.rows = rows; ln.C = a->C; ln.dtype = a->dtype; ln.eps = b->ln_eps;
-  layernorm_kernel<<<(int)((rows * 32 + 255) / 256), 256, 0, st>>>(ln);
+  launch_layernorm(ln, st);
   PA_CUDA_OK(cudaGetLastError());
   launch_counter()++;
   // x + proj(attention(img)): the residual rides in the proj GEMM's epilogue
@@ -1328,6 +1338,7 @@ int pa_cvt_fwd(const pa_cvt_args* a, void* workspace, size_t workspace_bytes, vo
   g.B = ob; g.ldb = C; g.b_batch = (long long)HW * C;
   g.D = a->y; g.ldd = HW; g.d_batch = (long long)C * HW;
   g.bias = a->proj_bias; g.bias_mode = a->proj_bias ? 2 : 0;
+  if (a->residual) { g.residual = a->residual; g.ldr = HW; g.r_batch = (long long)C * HW; g.res_dtype = a->dtype; }
   return gemm_impl(&g, st);
 }
 
@@ -1419,7 +1430,7 @@ int pa_xca_block_attn_fwd(const pa_xca_block_args* b, void* workspace, size_t wo
   void* img = ws.take((size_t)rows * a->C * 2);
   LnParams ln;
   ln.x = a->x; ln.out = img; ln.gamma = b->ln_weight; ln.beta = b->ln_bias; ln.rows = rows; ln.C = a->C; ln.dtype = a->dtype; ln.eps = b->ln_eps;
-  layernorm_kernel<<<(int)((rows * 32 + 255) / 256), 256, 0, st>>>(ln);
+  launch_layernorm(ln, st);
   PA_CUDA_OK(cudaGetLastError());
   launch_counter()++;
   return xca_run(a, img, PA_DTYPE_F16, a->x, ws.take(0), st);
@@ -1569,7 +1580,7 @@ int pa_cswin_block_attn_fwd(const pa_cswin_block_args* a, void* workspace, size_
   // img = norm1(x)   (cswin.py:184)
   LnParams ln;
   ln.x = a->x; ln.out = img; ln.gamma = a->norm1_weight; ln.beta = a->norm1_bias; ln.rows = rows; ln.C = C; ln.dtype = a->dtype; ln.eps = a->ln_eps;
-  layernorm_kernel<<<(int)((rows * 32 + 255) / 256), 256, 0, st>>>(ln);
+  launch_layernorm(ln, st);
   PA_CUDA_OK(cudaGetLastError());
   launch_counter()++;
   // qkv = Linear(C, 3C)(img), column o -> (s, c) = (o / C, o % C)   (cswin.py:185)

@@ -192,7 +192,6 @@ attn_proj_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // ---- head loop: S(h) and P V(h) are issued in whatever order their inputs become ready
       int ns = 0, npv = 0;
       while (npv < H) {
-        bool did = false;
         if (ns < H) {
           const int st = hc & 1;
           const uint32_t ph = (hc >> 1) & 1;
@@ -214,7 +213,6 @@ attn_proj_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             __syncwarp();
             if (st) ++su1; else ++su0;
             ++hc; ++ns;
-            did = true;
           }
         }
         if (npv < ns) {
@@ -234,7 +232,6 @@ attn_proj_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             __syncwarp();
             ++npv;
-            did = true;
           }
         }
       }

@@ -463,32 +463,67 @@ __device__ __forceinline__ void cs_attn_role(const CUtensorMap& tmQ, const CUten
     for (int u = worker; u < units; u += nworkers, ++it) {
       const int qt = u % p.q_tiles;
       const bool warp_active = (qt * 128 + q * 32) < p.n_q;
+      // additive score bias (RELPOS, cmt.py:100): this thread's row of rel_pos[h], columns from c_lo on, multiplied by 1 / scale
+      // when it is added to the raw scores -- both passes then run unchanged on s + r / scale.  With at most 64 keys (every CMT
+      // stage of the zoo has 49) the thread's <= 32 values are requested HERE, before the wait for S, and stay in registers for
+      // both passes (first version: 16 scalar loads per step inside each pass, every one an exposed L2 round trip -- the
+      // attention of a config-3-sized CMT forward took 565 us instead of 69)
+      const float* rp = nullptr;
+      float rb0[16], rb1[16];
+      const bool rel_pre = RELPOS && nst <= 2;
+      if constexpr (RELPOS) {
+        const int h = (u / p.q_tiles) % p.H;
+        const int row = min(qt * 128 + trow, p.n_q - 1);
+        rp = p.rel_pos + ((size_t)h * p.n_q + row) * p.n_k + c_lo;
+        if (rel_pre && warp_active) {
+          if ((p.n_k & 3) == 0) {                    // rows 16-byte aligned (c_lo is a multiple of 16 columns)
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 a = (i < nvalid) ? __ldg(reinterpret_cast<const float4*>(rp + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 b = (nst > 1 && 16 + i < nvalid) ? __ldg(reinterpret_cast<const float4*>(rp + 16 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              rb0[i] = a.x; rb0[i + 1] = a.y; rb0[i + 2] = a.z; rb0[i + 3] = a.w;
+              rb1[i] = b.x; rb1[i + 1] = b.y; rb1[i + 2] = b.z; rb1[i + 3] = b.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              rb0[i] = (i < nvalid) ? __ldg(rp + i) : 0.f;
+              rb1[i] = (nst > 1 && 16 + i < nvalid) ? __ldg(rp + 16 + i) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { rb0[i] *= p.rel_mul; rb1[i] *= p.rel_mul; }
+        }
+      }
       mbar_wait(s_full, it & 1);
       tc_fence_after();
       if (tracer) CS_TRACE_A(it, 2);
       // ---- pass 1: partial row max
       float mx = -INFINITY;
-      // additive score bias (RELPOS, cmt.py:100): this thread's row of rel_pos[h], columns from c_lo on, pre-multiplied by
-      // 1 / scale when it is added to the raw scores -- both passes then run unchanged on s + r / scale
-      const float* rp = nullptr;
-      if constexpr (RELPOS) {
-        const int h = (u / p.q_tiles) % p.H;
-        const int row = min(qt * 128 + trow, p.n_q - 1);
-        rp = p.rel_pos + ((size_t)h * p.n_q + row) * p.n_k + c_lo;
-      }
       if constexpr (RELPOS) {
         if (warp_active) {
 #pragma unroll 1
           for (int k = 0; k < nst; ++k) {
             uint32_t v[16];
-            float r[16];
             const int nv = nvalid - k * 16;
             tmem_ld16(t_my + k * 16, v);
+            if (rel_pre) {
+              tmem_ld_wait();
+              if (k == 0) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = (i < nv) ? __ldg(rp + k * 16 + i) * p.rel_mul : 0.f;
-            tmem_ld_wait();
+                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + rb0[i]);
+              } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + r[i]);
+                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + rb1[i]);
+              }
+            } else {
+              float r[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = (i < nv) ? __ldg(rp + k * 16 + i) * p.rel_mul : 0.f;
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + r[i]);
+            }
             mx = chunk_max<16>(v, nv, mx);
           }
         }
@@ -528,13 +563,24 @@ __device__ __forceinline__ void cs_attn_role(const CUtensorMap& tmQ, const CUten
         for (int k = 0; k < nst; ++k) {
           tmem_ld16(t_my + k * 16, va);
           if constexpr (RELPOS) {
-            float r[16];
-            const int nv = nvalid - k * 16;
+            if (rel_pre) {
+              tmem_ld_wait();
+              if (k == 0) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = (i < nv) ? __ldg(rp + k * 16 + i) * p.rel_mul : 0.f;
-            tmem_ld_wait();
+                for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) + rb0[i]);
+              } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) + r[i]);
+                for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) + rb1[i]);
+              }
+            } else {
+              float r[16];
+              const int nv = nvalid - k * 16;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = (i < nv) ? __ldg(rp + k * 16 + i) * p.rel_mul : 0.f;
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) + r[i]);
+            }
           } else {
             tmem_ld_wait();
           }

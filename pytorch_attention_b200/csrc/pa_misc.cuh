@@ -203,6 +203,62 @@ struct LnParams {
   const void* x; void* out; const float* gamma; const float* beta;
   long long rows; int C, dtype; float eps;
 };
+// Rows of at most NJ x 256 channels (NJ = 1..4): the row is read ONCE, as NJ 16-byte loads per lane that are all issued before
+// anything is reduced, and kept in NJ x 8 registers.  One instantiation per NJ keeps the register count at what the width needs
+// (the generic kernel below reserves 4 x 8 values and ran at 41 % of the warp slots / 39 % of the DRAM rate at C = 512).
+template <int NJ>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const LnParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (row >= p.rows) return;
+  const uint16_t* xr = reinterpret_cast<const uint16_t*>(p.x) + row * p.C;
+  uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + row * p.C;
+  uint4 raw[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int c = (j * 32 + lane) * 8;
+    raw[j] = (c < p.C) ? __ldg(reinterpret_cast<const uint4*>(xr + c)) : make_uint4(0, 0, 0, 0);
+  }
+  float f[NJ][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    unpack8(raw[j], p.dtype, f[j]);
+    if ((j * 32 + lane) * 8 < p.C) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += f[j][k];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / p.C;
+  float v = 0.f;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    if ((j * 32 + lane) * 8 < p.C) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v = fmaf(f[j][k] - mean, f[j][k] - mean, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = rsqrtf(v / p.C + p.eps);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int c = (j * 32 + lane) * 8;
+    if (c < p.C) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + c + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o8[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o8[k] = fmaf((f[j][k] - mean) * rstd, gg[k], bb[k]);
+      *reinterpret_cast<uint4*>(orow + c) = pack8(o8, 0);
+    }
+  }
+}
+
 __global__ void layernorm_kernel(const LnParams p) {
   // one warp per row; the row is read ONCE into registers (up to 4 x 8 elements per lane = C <= 1024), longer rows
   // fall back to re-reading.  Statistics in fp32, two-pass (mean, then centred variance) like ATen's layer_norm.

@@ -39,7 +39,7 @@ def dropin_class(variant):
     return {"vit": pa.vit.Attention, "vit_block": pa.vit.TransformerEncoder, "setr": pa.setr.Attention, "moat": pa.moat.Attention,
             "bvit": pa.bvit.Broad_Attention, "pvt": pa.pvt.Attention, "pvt_block": pa.pvt.Block, "segformer": pa.segformer.Attention, "cmt": pa.cmt.Attention,
             "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention, "cswin_block": pa.cswin.CSWinBlock, "xca": pa.xcit.XCA,
-            "xca_block": pa.xcit.XCABlockAttentionHalf, "class_attn": pa.xcit.ClassAttention}[variant]
+            "xca_block": pa.xcit.XCABlockAttentionHalf, "pam": pa.dual_attention.PAM, "class_attn": pa.xcit.ClassAttention}[variant]
 
 
 def build_dropin(spec, params, out_dtype=None):

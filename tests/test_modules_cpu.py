@@ -186,3 +186,13 @@ def test_bvit_broad_attention_matches_live_reference_contract(kw):
     assert {k: v.shape for k, v in r.state_dict().items()} == {k: v.shape for k, v in m.state_dict().items()}
     m.load_state_dict(r.state_dict())
     assert isinstance(m.to_out, torch.nn.Identity) == isinstance(r.to_out, torch.nn.Identity)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
+def test_pam_matches_live_reference_contract():
+    from oracle.cases import load_reference_class
+    ref = load_reference_class(REF, "dual_attention", "PAM")
+    assert str(inspect.signature(ref.__init__)) == str(inspect.signature(pa.dual_attention.PAM.__init__))
+    r, m = ref(64), pa.dual_attention.PAM(64)
+    assert {k: v.shape for k, v in r.state_dict().items()} == {k: v.shape for k, v in m.state_dict().items()}
+    m.load_state_dict(r.state_dict())

@@ -117,6 +117,28 @@ def main():
     B, C, Hh = 64, 384, 14
     run("CvT B=64 C=384 14x14 H=6", pa.cvt.Attention(C, 6), torch.randn(B, C, Hh, Hh, device=dev).half(), lambda m, x: m(x),
         B * Hh * Hh, B * (8 * Hh * Hh * C * C + 4 * (Hh * Hh) ** 2 * C + 18 * Hh * Hh * C))
+    B, N, C = 64, 197, 768
+    run("ClassAttention B=64 N=197 C=768 H=12", pa.xcit.ClassAttention(C, 12), torch.randn(B, N, C, device=dev).half(), lambda m, x: m(x),
+        B * N, B * (6 * N * C * C + 2 * C * C + 4 * N * C))
+    # round-2 siblings / block halves (rows f-1, f-2, f-4): same geometry as C3 / XCA / C2 so the lines compare
+    B, Hh, Ww, C, sr = 32, 64, 64, 512, 8
+    N, M = Hh * Ww, (Hh // sr) * (Ww // sr)
+    pvt_flops = B * (4 * N * C * C + 4 * M * C * C + 4 * N * M * C)
+    run("SegFormer Attention sr=8 B=32 64x64 C=512 H=8 (dense reduction conv)", pa.segformer.Attention(C, 8, sr_ratio=sr),
+        torch.randn(B, N, C, device=dev).half(), lambda mod, x: mod(x, Hh, Ww), B * N, pvt_flops + B * 2 * M * C * C * sr * sr)
+    rel = torch.randn(8, N, M, device=dev)
+    run("CMT Attention sr=8 B=32 64x64 C=512 H=8 (+ relative_pos)", pa.cmt.Attention(C, 8, sr_ratio=sr),
+        torch.randn(B, N, C, device=dev).half(), lambda mod, x: mod(x, Hh, Ww, rel), B * N, pvt_flops + B * 2 * M * C * sr * sr)
+    run("pvt.Block attention half sr=8 B=32 64x64 C=512 H=8 (LN + residual)", pa.pvt.Block(C, 8, sr_ratio=sr),
+        torch.randn(B, N, C, device=dev).half(), lambda mod, x: mod.attention_half(x, Hh, Ww), B * N, pvt_flops + B * 2 * M * C * sr * sr)
+    B, N, C = 64, 196, 768
+    run("XCABlock attention half B=64 N=196 C=768 H=12 (LN + LayerScale + residual)", pa.xcit.XCABlockAttentionHalf(C, 12, eta=1.0),
+        torch.randn(B, N, C, device=dev).half(), lambda m, x: m(x), B * N, B * (8 * N * C * C + 4 * N * C * 64))
+    B, N, C = 64, 197, 768
+    run("ViT TransformerEncoder attention half B=64 N=197 C=768 H=12 (LN + residual)", pa.vit.TransformerEncoder(C, 12),
+        torch.randn(B, N, C, device=dev).half(), lambda m, x: m.attention_half(x), B * N, B * (8 * N * C * C + 4 * N * N * C))
+    run("bvit.Broad_Attention B=64 N=197 dim=768 heads=12 dim_head=64", pa.bvit.Broad_Attention(C, 12, 64),
+        torch.randn(B, N, C, device=dev).half(), lambda m, x: m(x)[0], B * N, B * (8 * N * C * C + 4 * N * N * C))
 
 
 if __name__ == "__main__":
