@@ -143,8 +143,30 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));   // * 2^n
 }
 
-// Stage A of the skewed pass 2: e = exp2(s * sl2 - mxs) for the first nval columns of a 16-column step (0 beyond)
+// ---- pass 2 of the row softmax, one 16-column step:  p = exp2(s * sl2 - mxs), fp16 P packed in pairs, partial row sums.
+// PA_EXP_F16X2=1 (opt-in at compile time): the exponent x is computed in fp32, rounded to a half pair and exponentiated by ONE packed MUFU
+// op per two scores (ex2.approx.f16x2); the result IS the packed fp16 P.  The exp pass is MUFU-bound (two softmax warps per
+// scheduler, 16 ex2 / clk / SM): half the MUFU instructions.  Accuracy: P is rounded to fp16 either way; rounding x to half adds a
+// relative error of ln2 * ulp(x) / 2 <= 3.4e-4 for the terms that matter (x in [-2, 0]) and more only where 2^x < 2^-2^k is
+// small in proportion -- measured against the oracle in tests/ (bar 1e-3).
+// PA_EXP_F16X2=0 (default): fp32 MUFU ex2 for 12 of 16 scores and a degree-3 polynomial on the FMA pipe for the other 4 (round 1).
+// MEASURED (late round 2): parity green with PA_EXP_F16X2=1 (142 GPU tests), speed unchanged or slightly worse (ViT-B attention core
+// 28.1 -> 29.2 us, CSWin C4 3669 -> 3722 us): ptxas splits ex2.approx.f16x2 into TWO MUFU.EX2.F16 -- 16 MUFU ops per 16 scores
+// against 12 + 4 polynomials -- and MUFU.EX2.F16 issues at the fp32 rate on sm_100a.  Default stays 0.
+#ifndef PA_EXP_F16X2
+#define PA_EXP_F16X2 0
+#endif
+// Stage A: e = the exponent (PA_EXP_F16X2) or the exponential (fp32 path) of the first nval columns (-inf / 0 beyond)
 __device__ __forceinline__ void exp_stage(const uint32_t (&v)[16], float (&e)[16], int nval, float sl2, float mxs, int dbg = 0) {
+#if PA_EXP_F16X2
+  if (nval >= 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) e[i] = fmaf(__uint_as_float(v[i]), sl2, -mxs);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) e[i] = (i < nval) ? fmaf(__uint_as_float(v[i]), sl2, -mxs) : -INFINITY;   // 2^-inf = 0: padded keys
+  }
+#else
   if (dbg & 1) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) e[i] = fmaf(__uint_as_float(v[i]), sl2, -mxs);
@@ -162,15 +184,29 @@ __device__ __forceinline__ void exp_stage(const uint32_t (&v)[16], float (&e)[16
       if (i < nval) e[i] = ex2f(fmaf(__uint_as_float(v[i]), sl2, -mxs));   // nval is warp-uniform; padded keys never reach the MUFU
     }
   }
+#endif
 }
-// Stage B: row-partial sum + fp16 pack of a step whose exponentials were issued one step earlier
+// Stage B: fp16 pack (PA_EXP_F16X2: + the packed exponential) and row-partial sums of a step
 __device__ __forceinline__ void pack_stage(const float (&e)[16], uint32_t (&pk)[8], float& s0, float& s1) {
+#if PA_EXP_F16X2
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    __half2 h = __floats2half2_rn(e[i], e[i + 1]);
+    uint32_t r;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<uint32_t*>(&h)));
+    pk[i >> 1] = r;
+    const float2 f = __half22float2(*reinterpret_cast<__half2*>(&r));
+    s0 += f.x;
+    s1 += f.y;
+  }
+#else
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
     s0 += e[i];
     s1 += e[i + 1];
     pk[i >> 1] = pack_h2(e[i], e[i + 1]);
   }
+#endif
 }
 
 __device__ __forceinline__ void attn_init_barriers(uint64_t* bars) {     // one thread; bars: 16 mbarriers

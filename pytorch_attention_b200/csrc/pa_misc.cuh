@@ -80,6 +80,9 @@ __global__ void sr_conv_bn_kernel(const SrParams p) {
   }
 }
 
+// (measured and rejected, late round 2: one block per output token with (channel groups) x (tap rows) threads and the sr partial
+//  sums meeting in shared memory -- every load of a token in flight at once, 2048 blocks x 512 threads at config 3 -- is slower
+//  than the one-thread-per-output loop above: C3 forward 255 us against 248.)
 // SegFormer spatial reduction (segformer.py:27, 38-39): a DENSE conv with k = stride = sr is a GEMM over non-overlapping
 // patches.  This kernel lays the patches out as that GEMM's K-major A operand -- a pure re-partition of x (kernel == stride:
 // every element of x moves exactly once):  out[b, i*Ws+j, (u*sr+v)*C + c] = x[b, (sr*i+u)*W + sr*j+v, c]
