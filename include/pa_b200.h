@@ -185,6 +185,9 @@ typedef struct {
   const float* rel_pos;      /* cmt.Attention.forward(x, H, W, relative_pos), cmt.py:100: fp32 [H, N, M] added to
                                 q k^T * scale before the softmax (M = key tokens after the reduction), or NULL.
                                 Needs 64-wide heads and M <= 240 */
+  const void* kv_tokens;     /* NULL, or fp16 [B, kv_count, C]: keys / values are projected from THESE tokens instead of from x
+                                (sr must be 1; kv_weight fp16) -- the pooled pyramid of p2t.PoolingAttention, see pa_p2t_fwd */
+  int kv_count;
 } pa_pvt_args;
 size_t pa_pvt_workspace_bytes(const pa_pvt_args* a);
 int pa_pvt_fwd(const pa_pvt_args* a, void* workspace, size_t workspace_bytes, void* stream);
@@ -201,6 +204,26 @@ typedef struct {
 } pa_pvt_block_args;
 size_t pa_pvt_block_attn_workspace_bytes(const pa_pvt_block_args* a);
 int pa_pvt_block_attn_fwd(const pa_pvt_block_args* a, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- p2t.PoolingAttention  (p2t.py:46-94) */
+/* Keys / values come from a pooling pyramid of the token map (p2t.py:78-86): per level l
+ *     pool_l = adaptive_avg_pool2d(x as [B,C,H,W], (pool_h[l], pool_w[l]));  pool_l += d_convs[l](pool_l)   (depthwise 3x3, zero pad)
+ * the levels concatenated along the token axis, LayerNorm over the channels, then kv = Linear(C, 2C).  Two small kernels build
+ * those tokens (adaptive average straight from the token-major x; depthwise conv + skip + LayerNorm, one warp per pooled token),
+ * the rest is the PVT path with `kv_tokens`: GEMM(q) -> GEMM(kv) -> attention core -> GEMM(proj). */
+typedef struct {
+  pa_pvt_args attn;          /* B, N = Himg*Wimg, C, H, scale, x, q_weight / q_bias, kv_weight (fp16 [2C,C] = kv.0.weight) / kv_bias,
+                                proj_*, y; sr = 1, sr_mode = 0, kv_tokens / kv_count are filled in by the library */
+  int n_levels;              /* 1..4 */
+  int pool_h[4], pool_w[4];  /* round(H / pool_ratio), round(W / pool_ratio) per level (p2t.py:80) */
+  const float* dconv_weight_t[4];   /* per level [9, C] fp32: d_convs[l].weight [C,1,3,3] transposed */
+  const float* dconv_bias[4];       /* per level [C] fp32 or NULL */
+  const float* norm_weight;  /* [C] self.norm (p2t.py:74) */
+  const float* norm_bias;
+  float norm_eps;
+} pa_p2t_args;
+size_t pa_p2t_workspace_bytes(const pa_p2t_args* a);
+int pa_p2t_fwd(const pa_p2t_args* a, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- cvt.Attention  (cvt.py:48-76), NCHW in and out */
 typedef struct {

@@ -374,3 +374,45 @@ def pam_attention(x, b_weight, b_bias, c_weight, c_bias, d_weight, d_bias, alpha
     p = _softmax_last(torch.einsum("bci,bcj->bij", B_, C_))
     y = torch.einsum("bij,bcj->bci", p, D_).reshape(n, c, h, w)
     return alpha * y + x
+
+
+# --------------------------------------------------------------------------
+# P2T pooling attention (reference: vision_transformers/p2t.py:46-94)
+# --------------------------------------------------------------------------
+def _adaptive_avg_pool2d(t, oh, ow):
+    """F.adaptive_avg_pool2d on [B,C,H,W]: output (i, j) averages rows [floor(i*H/oh), ceil((i+1)*H/oh)) x the same in W."""
+    B, C, H, W = t.shape
+    out = t.new_zeros(B, C, oh, ow)
+    for i in range(oh):
+        h0, h1 = (i * H) // oh, -((-(i + 1) * H) // oh)
+        for j in range(ow):
+            w0, w1 = (j * W) // ow, -((-(j + 1) * W) // ow)
+            out[:, :, i, j] = t[:, :, h0:h1, w0:w1].mean(dim=(2, 3))
+    return out
+
+
+def p2t_pooling_attention(x, H_img, W_img, q_weight, q_bias, kv_weight, kv_bias, proj_weight, proj_bias, norm_weight, norm_bias,
+                          num_heads, pool_ratios, dconv_weights, dconv_biases, scale=None, eps=1e-5):
+    """PoolingAttention.forward(x, H, W, d_convs) (p2t.py:74-94).  dconv_weights[i]: [C,1,3,3] depthwise, zero pad 1."""
+    B, N, C = x.shape
+    nh = num_heads
+    hd = C // nh
+    scale = scale or hd ** -0.5
+    q = _lin(x, q_weight, q_bias).reshape(B, N, nh, hd)                     # p2t.py:76
+    x_ = x.permute(0, 2, 1).reshape(B, C, H_img, W_img)
+    pools = []
+    for r, w, b in zip(pool_ratios, dconv_weights, dconv_biases):
+        pool = _adaptive_avg_pool2d(x_, round(H_img / r), round(W_img / r))  # p2t.py:80
+        pool = pool + _dwconv_same(pool, w, b, 3)                             # p2t.py:81
+        pools.append(pool.reshape(B, C, -1))
+    pools = torch.cat(pools, dim=2).permute(0, 2, 1)                         # [B, M, C]  p2t.py:84-85
+    mu = pools.mean(dim=-1, keepdim=True)
+    var = ((pools - mu) ** 2).mean(dim=-1, keepdim=True)
+    pools = (pools - mu) / torch.sqrt(var + eps) * norm_weight + norm_bias
+    M = pools.shape[1]
+    kv = _lin(pools, kv_weight, kv_bias).reshape(B, M, 2, nh, hd)            # p2t.py:87
+    k, v = kv[:, :, 0], kv[:, :, 1]
+    s = torch.einsum("bnhd,bmhd->bhnm", q, k) * scale
+    p = _softmax_last(s)
+    o = torch.einsum("bhnm,bmhd->bnhd", p, v).reshape(B, N, C)
+    return _lin(o, proj_weight, proj_bias)

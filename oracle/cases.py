@@ -26,6 +26,11 @@ GOLDEN_CASES = {
     # bvit.Broad_Attention(dim, heads, dim_head): inner width != dim, (out, q, k, v) returned     bvit.py:49-76
     "bvit_b2_n65_c192_h3_hd64": dict(variant="bvit", ctor=dict(dim=192, heads=3, dim_head=64), x=(2, 65, 192)),
     "bvit_b2_n50_c96_h4_hd32": dict(variant="bvit", ctor=dict(dim=96, heads=4, dim_head=32), x=(2, 50, 96)),
+    # dilateformer.GlobalAttention(dim, num_heads=8): ViT's math on [B, H, W, C]          dilateformer.py:136-164
+    "dilateformer_b2_12x12_c128_h2": dict(variant="dilateformer", ctor=dict(dim=128, num_heads=2, qkv_bias=True), x=(2, 12, 12, 128)),
+    # p2t.PoolingAttention(dim, num_heads, pool_ratios).forward(x, H, W, d_convs): keys / values from a pooling pyramid   p2t.py:46-94
+    "p2t_b2_14x14_c128_h2": dict(variant="p2t", ctor=dict(dim=128, num_heads=2, qkv_bias=True, pool_ratios=[1, 2, 3, 6]), x=(2, 196, 128), hw=(14, 14)),
+    "p2t_b2_12x20_c64_h1_ratios_3_4_5": dict(variant="p2t", ctor=dict(dim=64, num_heads=1, pool_ratios=[3, 4, 5]), x=(2, 240, 64), hw=(12, 20)),
     # pvt.Attention(dim, num_heads, sr_ratio)            pvt.py:52-91
     "pvt_b2_16x16_c128_h2_sr4": dict(variant="pvt", ctor=dict(dim=128, num_heads=2, sr_ratio=4), x=(2, 256, 128), hw=(16, 16)),
     "pvt_b2_8x8_c128_h2_sr1_bias": dict(variant="pvt", ctor=dict(dim=128, num_heads=2, sr_ratio=1, qkv_bias=True), x=(2, 64, 128), hw=(8, 8)),
@@ -65,6 +70,8 @@ _REF_CLASS = {
     "setr": ("setr", "Attention"),
     "moat": ("moat", "Attention"),
     "bvit": ("bvit", "Broad_Attention"),
+    "dilateformer": ("dilateformer", "GlobalAttention"),
+    "p2t": ("p2t", "PoolingAttention"),
     "pvt": ("pvt", "Attention"),
     "pvt_block": ("pvt", "Block"),
     "segformer": ("segformer", "Attention"),
@@ -127,13 +134,31 @@ def make_inputs(spec, seed=0):
         N = spec["x"][1]
         M = N // (c.get("sr_ratio", 1) ** 2)
         out["relative_pos"] = round_fp16_(torch.randn(c["num_heads"], N, M, generator=g))
+    if spec["variant"] == "p2t":
+        # the model's d_convs (p2t.py: one depthwise 3x3 conv per pool ratio, owned by the stage and passed to every block)
+        c = spec["ctor"]
+        L_ = len(c["pool_ratios"])
+        out["dconv_weight"] = round_fp16_(torch.randn(L_, c["dim"], 1, 3, 3, generator=g) / 3.0)
+        out["dconv_bias"] = round_fp16_(torch.randn(L_, c["dim"], generator=g) * 0.05)
     return out
+
+
+def p2t_d_convs(inputs, device="cpu"):
+    """nn.Conv2d(dim, dim, 3, 1, 1, groups=dim) modules holding a p2t case's d_conv tensors."""
+    w, b = inputs["dconv_weight"].float(), inputs["dconv_bias"].float()
+    convs = torch.nn.ModuleList()
+    for i in range(w.shape[0]):
+        m = torch.nn.Conv2d(w.shape[1], w.shape[1], 3, 1, 1, groups=w.shape[1])
+        with torch.no_grad():
+            m.weight.copy_(w[i]); m.bias.copy_(b[i])
+        convs.append(m)
+    return convs.to(device)
 
 
 def load_reference(ref_path):
     if ref_path not in sys.path:
         sys.path.insert(0, ref_path)
-    return {m: importlib.import_module(m) for m in ("ViT", "pvt", "cvt", "cswin", "xcit", "moat", "segformer", "cmt", "bvit")}
+    return {m: importlib.import_module(m) for m in ("ViT", "pvt", "cvt", "cswin", "xcit", "moat", "segformer", "cmt", "bvit", "p2t")}
 
 
 def load_reference_class(ref_path, module, cls):
@@ -146,15 +171,23 @@ def load_reference_class(ref_path, module, cls):
         if am not in sys.path:
             sys.path.insert(0, am)
         return getattr(importlib.import_module(module), cls)
-    if module != "setr":
+    if module not in ("setr", "dilateformer"):
         return getattr(load_reference(ref_path)[module], cls)
+    # setr.py builds and runs a whole SETR model at import time (setr.py:131-134); dilateformer.py imports timm, which this
+    # image does not have (dilateformer.py:19-20).  For those two files the module's imports (those that resolve) and its own
+    # class / function definitions are executed one by one -- still the reference's code, read from where it lies.
     import ast
     import os
     src = open(os.path.join(ref_path, module + ".py")).read()
     tree = ast.parse(src)
-    keep = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom, ast.ClassDef, ast.FunctionDef))]
     ns = {"__name__": "reference_" + module}
-    exec(compile(ast.Module(body=keep, type_ignores=[]), os.path.join(ref_path, module + ".py"), "exec"), ns)
+    for n in tree.body:
+        if isinstance(n, (ast.Import, ast.ImportFrom, ast.ClassDef, ast.FunctionDef)):
+            try:
+                exec(compile(ast.Module(body=[n], type_ignores=[]), os.path.join(ref_path, module + ".py"), "exec"), ns)
+            except (ImportError, NameError):
+                if isinstance(n, ast.ClassDef) and n.name == cls:
+                    raise
     return ns[cls]
 
 
@@ -168,6 +201,8 @@ def reference_forward(spec, mod, x, inputs=None):
         if v == "pvt_block":
             # attention half only (pvt.py:106), with the reference block's own sub-modules
             return x + mod.attn(mod.norm1(x), *spec["hw"])
+        if v == "p2t":
+            return mod(x, *spec["hw"], d_convs=p2t_d_convs(inputs))
         if v == "bvit":
             return mod(x)[0]           # (out, q, k, v): the golden file pins out; q/k/v are checked in tests/test_oracle_vs_reference.py
         if v == "xca_block":
@@ -232,6 +267,19 @@ def run_oracle_case(spec, inputs, params, dtype=torch.float32):
                  "sr.0.weight", "sr.0.bias", "sr.1.weight", "sr.1.bias", "sr.1.running_mean", "sr.1.running_var")
         return A.pvt_attention(x, spec["hw"][0], spec["hw"][1], num_heads=c["num_heads"],
                                sr_ratio=c.get("sr_ratio", 1), **kw)
+    if v == "p2t":
+        L_ = len(c["pool_ratios"])
+        dw, db = inputs["dconv_weight"].to(dtype), inputs["dconv_bias"].to(dtype)
+        return A.p2t_pooling_attention(x, spec["hw"][0], spec["hw"][1], P["q.0.weight"], P.get("q.0.bias"), P["kv.0.weight"],
+                                       P.get("kv.0.bias"), P["proj.weight"], P["proj.bias"], P["norm.weight"], P["norm.bias"],
+                                       c["num_heads"], c["pool_ratios"], [dw[i] for i in range(L_)], [db[i] for i in range(L_)],
+                                       c.get("qk_scale"))
+    if v == "dilateformer":
+        # dilateformer.py:151-162: ViT.Attention over the H * W positions of a channels-last image
+        B_, H_, W_, C_ = x.shape
+        scale = c.get("qk_scale") or None
+        return A.vit_attention(x.reshape(B_, H_ * W_, C_), P["qkv.weight"], P.get("qkv.bias"), P["proj.weight"], P["proj.bias"],
+                               c.get("num_heads", 8), scale).reshape(B_, H_, W_, C_)
     if v == "pam":
         return A.pam_attention(x, P["b.weight"], P["b.bias"], P["c.weight"], P["c.bias"], P["d.weight"], P["d.bias"], P["alpha"])
     if v == "bvit":

@@ -55,7 +55,13 @@ class PvtArgs(C.Structure):
                 ("x", _vp), ("q_weight", _vp), ("q_bias", _vp), ("kv_weight", _vp), ("kv_bias", _vp),
                 ("proj_weight", _vp), ("proj_bias", _vp), ("sr_weight_t", _vp), ("sr_scale", _vp), ("sr_shift", _vp),
                 ("y", _vp),
-                ("sr_mode", _i), ("sr_dense_weight", _vp), ("sr_dense_bias", _vp), ("rel_pos", _vp)]
+                ("sr_mode", _i), ("sr_dense_weight", _vp), ("sr_dense_bias", _vp), ("rel_pos", _vp),
+                ("kv_tokens", _vp), ("kv_count", _i)]
+
+
+class P2tArgs(C.Structure):
+    _fields_ = [("attn", PvtArgs), ("n_levels", _i), ("pool_h", _i * 4), ("pool_w", _i * 4),
+                ("dconv_weight_t", _vp * 4), ("dconv_bias", _vp * 4), ("norm_weight", _vp), ("norm_bias", _vp), ("norm_eps", _f)]
 
 
 class PvtBlockArgs(C.Structure):
@@ -117,6 +123,8 @@ SYMBOLS = {
     "pa_bvit_fwd": (_i, [C.POINTER(BvitArgs), _vp, C.c_size_t, _vp]),
     "pa_pvt_workspace_bytes": (C.c_size_t, [C.POINTER(PvtArgs)]),
     "pa_pvt_fwd": (_i, [C.POINTER(PvtArgs), _vp, C.c_size_t, _vp]),
+    "pa_p2t_workspace_bytes": (C.c_size_t, [C.POINTER(P2tArgs)]),
+    "pa_p2t_fwd": (_i, [C.POINTER(P2tArgs), _vp, C.c_size_t, _vp]),
     "pa_pvt_block_attn_workspace_bytes": (C.c_size_t, [C.POINTER(PvtBlockArgs)]),
     "pa_pvt_block_attn_fwd": (_i, [C.POINTER(PvtBlockArgs), _vp, C.c_size_t, _vp]),
     "pa_cvt_workspace_bytes": (C.c_size_t, [C.POINTER(CvtArgs)]),

@@ -1150,7 +1150,10 @@ static int pvt_check(const pa_pvt_args* a) {
   if (a->dtype != PA_DTYPE_F16 && a->dtype != PA_DTYPE_BF16) return fail(PA_ERR_UNSUPPORTED, "pa_pvt: dtype must be fp16/bf16");
   return PA_OK;
 }
-static inline int pvt_m(const pa_pvt_args* a) { return a->sr > 1 ? (a->Himg / a->sr) * (a->Wimg / a->sr) : a->N; }
+static inline int pvt_m(const pa_pvt_args* a) {
+  if (a->kv_tokens) return a->kv_count;
+  return a->sr > 1 ? (a->Himg / a->sr) * (a->Wimg / a->sr) : a->N;
+}
 
 static int pvt_check_full(const pa_pvt_args* a) {
   int rc = pvt_check(a);
@@ -1158,6 +1161,7 @@ static int pvt_check_full(const pa_pvt_args* a) {
   if (a->sr_mode != 0 && a->sr_mode != 1) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: sr_mode must be 0 (depthwise + BatchNorm) or 1 (dense conv)");
   if (a->sr > 1 && (a->Himg % a->sr || a->Wimg % a->sr))
     return fail(PA_ERR_BAD_SHAPE, "pa_pvt: H=%d, W=%d not divisible by sr_ratio %d", a->Himg, a->Wimg, a->sr);
+  if (a->kv_tokens && (a->sr != 1 || a->kv_count <= 0)) return fail(PA_ERR_BAD_SHAPE, "pa_pvt: kv_tokens needs sr == 1 and kv_count > 0");
   return PA_OK;
 }
 
@@ -1183,6 +1187,7 @@ static int pvt_run(const pa_pvt_args* a, const void* x_in, int x_dtype, const vo
   void* kv = ws.take((size_t)mrows * 2 * C * 2);
   const void* kv_in = x_in;
   int kv_dtype = x_dtype;
+  if (a->kv_tokens) { kv_in = a->kv_tokens; kv_dtype = PA_DTYPE_F16; }     // p2t: keys / values from the pooled pyramid
   if (a->sr > 1 && a->sr_mode == 0) {
     // spatial reduction: depthwise conv (k = stride = sr) + eval BatchNorm folded into scale/shift   (pvt.py:77-78, cmt.py:97-98)
     SrParams sp;
@@ -1244,6 +1249,78 @@ int pa_pvt_fwd(const pa_pvt_args* a, void* workspace, size_t workspace_bytes, vo
   if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_pvt_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
   if ((rc = current_device_check())) return rc;
   return pvt_run(a, a->x, a->dtype, nullptr, workspace, (cudaStream_t)stream);
+}
+
+// ================================================================ P2T  (p2t.py:46-94)
+static int p2t_check(const pa_p2t_args* a, int* M_out) {
+  if (!a) return fail(PA_ERR_NULL, "pa_p2t: args is NULL");
+  int rc = pvt_check(&a->attn);
+  if (rc) return rc;
+  if (a->attn.sr != 1 || a->attn.sr_mode != 0 || a->attn.rel_pos) return fail(PA_ERR_BAD_SHAPE, "pa_p2t: attn.sr must be 1 (no reduction conv, no relative_pos)");
+  if (a->n_levels < 1 || a->n_levels > 4) return fail(PA_ERR_BAD_SHAPE, "pa_p2t: n_levels must be 1..4");
+  int M = 0;
+  for (int l = 0; l < a->n_levels; ++l) {
+    if (a->pool_h[l] < 1 || a->pool_w[l] < 1 || a->pool_h[l] > a->attn.Himg || a->pool_w[l] > a->attn.Wimg)
+      return fail(PA_ERR_BAD_SHAPE, "pa_p2t: pooled size %dx%d of level %d must lie in [1, H] x [1, W]", a->pool_h[l], a->pool_w[l], l);
+    M += a->pool_h[l] * a->pool_w[l];
+  }
+  *M_out = M;
+  return PA_OK;
+}
+
+static pa_pvt_args p2t_attn_args(const pa_p2t_args* a, int M, const void* tokens) {
+  pa_pvt_args at = a->attn;
+  at.kv_tokens = tokens ? tokens : reinterpret_cast<const void*>(16);     // workspace sizing only needs it non-NULL
+  at.kv_count = M;
+  return at;
+}
+
+size_t pa_p2t_workspace_bytes(const pa_p2t_args* a) {
+  int M = 0;
+  if (p2t_check(a, &M)) return 0;
+  const pa_pvt_args at = p2t_attn_args(a, M, nullptr);
+  const size_t mrows = (size_t)a->attn.B * M;
+  return align_up(mrows * a->attn.C * 4, 1024) + align_up(mrows * a->attn.C * 2, 1024) + pa_pvt_workspace_bytes(&at);
+}
+
+int pa_p2t_fwd(const pa_p2t_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+  int M = 0;
+  int rc = p2t_check(a, &M);
+  if (rc) return rc;
+  if (!a->attn.x || !a->attn.q_weight || !a->attn.kv_weight || !a->attn.proj_weight || !a->attn.y || !a->norm_weight || !a->norm_bias)
+    return fail(PA_ERR_NULL, "pa_p2t_fwd: x/weights/norm/y must be non-NULL");
+  for (int l = 0; l < a->n_levels; ++l)
+    if (!a->dconv_weight_t[l]) return fail(PA_ERR_NULL, "pa_p2t_fwd: dconv_weight_t[%d] is NULL", l);
+  const size_t need = pa_p2t_workspace_bytes(a);
+  if (!workspace || workspace_bytes < need) return fail(PA_ERR_WORKSPACE, "pa_p2t_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+  if ((rc = current_device_check())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = a->attn.C;
+  const long long mrows = (long long)a->attn.B * M;
+  Arena ws(workspace);
+  float* pooled = reinterpret_cast<float*>(ws.take((size_t)mrows * C * 4));
+  void* tokens = ws.take((size_t)mrows * C * 2);
+  P2tPoolParams pp = {};
+  P2tTokParams tp = {};
+  pp.x = a->attn.x; pp.pooled = pooled; pp.B = a->attn.B; pp.H = a->attn.Himg; pp.W = a->attn.Wimg; pp.C = C; pp.dtype = a->attn.dtype;
+  pp.n_levels = a->n_levels; pp.M = M;
+  tp.pooled = pooled; tp.out = tokens; tp.gamma = a->norm_weight; tp.beta = a->norm_bias; tp.eps = a->norm_eps;
+  tp.B = a->attn.B; tp.C = C; tp.n_levels = a->n_levels; tp.M = M;
+  int off = 0;
+  for (int l = 0; l < a->n_levels; ++l) {
+    pp.ph[l] = tp.ph[l] = a->pool_h[l]; pp.pw[l] = tp.pw[l] = a->pool_w[l]; pp.off[l] = tp.off[l] = off;
+    tp.w[l] = a->dconv_weight_t[l]; tp.bias[l] = a->dconv_bias[l];
+    off += a->pool_h[l] * a->pool_w[l];
+  }
+  // pooling pyramid -> normalised tokens   (p2t.py:78-86)
+  p2t_pool_kernel<<<grid_for(mrows * (C / 8), 256), 256, 0, st>>>(pp);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  p2t_tokens_kernel<<<(int)((mrows * 32 + 255) / 256), 256, 0, st>>>(tp);
+  PA_CUDA_OK(cudaGetLastError());
+  launch_counter()++;
+  const pa_pvt_args at = p2t_attn_args(a, M, tokens);
+  return pvt_run(&at, at.x, at.dtype, nullptr, ws.take(0), st);     // q, kv, attention, proj   (p2t.py:76, 88-94)
 }
 
 // ================================================================ pvt.Block / segformer.Block / cmt.Block, attention half

@@ -83,6 +83,89 @@ __global__ void sr_conv_bn_kernel(const SrParams p) {
 // (measured and rejected, late round 2: one block per output token with (channel groups) x (tap rows) threads and the sr partial
 //  sums meeting in shared memory -- every load of a token in flight at once, 2048 blocks x 512 threads at config 3 -- is slower
 //  than the one-thread-per-output loop above: C3 forward 255 us against 248.)
+// P2T pooling pyramid (p2t.py:78-86), kernel 1: adaptive_avg_pool2d of the token map at up to four output sizes.  Output
+// position (pi, pj) of level l averages rows [floor(pi*H/ph), ceil((pi+1)*H/ph)) x cols [floor(pj*W/pw), ceil((pj+1)*W/pw))
+// (ATen's adaptive pooling windows).  One thread = 8 consecutive channels of one pooled token, fp32 out [B, M, C].
+struct P2tPoolParams {
+  const void* x; float* pooled;
+  int B, H, W, C, dtype, n_levels, M;
+  int ph[4], pw[4], off[4];        // level sizes and first token index of each level
+};
+__global__ void p2t_pool_kernel(const P2tPoolParams p) {
+  const int cvec = p.C / 8;
+  const long long total = (long long)p.B * p.M * cvec;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvec);
+    long long t = idx / cvec;
+    const int tok = (int)(t % p.M);
+    const int b = (int)(t / p.M);
+    int l = 0;
+    while (l + 1 < p.n_levels && tok >= p.off[l + 1]) ++l;
+    const int r = tok - p.off[l], pi = r / p.pw[l], pj = r - pi * p.pw[l];
+    const int h0 = (pi * p.H) / p.ph[l], h1 = ((pi + 1) * p.H + p.ph[l] - 1) / p.ph[l];
+    const int w0 = (pj * p.W) / p.pw[l], w1 = ((pj + 1) * p.W + p.pw[l] - 1) / p.pw[l];
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int hh = h0; hh < h1; ++hh)
+      for (int ww = w0; ww < w1; ++ww) {
+        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.x) +
+                                                              ((long long)b * p.H * p.W + (long long)hh * p.W + ww) * p.C + cv * 8));
+        float xf[8];
+        unpack8(xv, p.dtype, xf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += xf[k];
+      }
+    const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+    float4* dst = reinterpret_cast<float4*>(p.pooled + ((long long)b * p.M + tok) * p.C + cv * 8);
+    dst[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+    dst[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+  }
+}
+// kernel 2: pool + depthwise3x3(pool) (+ bias, zero pad inside the level's own map), then LayerNorm over the channels
+// (two-pass statistics like layernorm_kernel), fp16 tokens [B, M, C].  One warp per pooled token; the maps are tiny.
+struct P2tTokParams {
+  const float* pooled; void* out;
+  const float* w[4]; const float* bias[4];     // per level [9, C] / [C]
+  const float* gamma; const float* beta; float eps;
+  int B, C, n_levels, M;
+  int ph[4], pw[4], off[4];
+};
+__device__ __forceinline__ float p2t_token_value(const P2tTokParams& p, const float* base, int l, int pi, int pj, int c) {
+  float v = base[((long long)pi * p.pw[l] + pj) * p.C + c];
+  float conv = p.bias[l] != nullptr ? __ldg(p.bias[l] + c) : 0.f;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int y = pi + dy, x = pj + dx;
+      if (y >= 0 && y < p.ph[l] && x >= 0 && x < p.pw[l])
+        conv = fmaf(__ldg(p.w[l] + ((dy + 1) * 3 + dx + 1) * p.C + c), base[((long long)y * p.pw[l] + x) * p.C + c], conv);
+    }
+  return v + conv;                    // pool + l(pool)   (p2t.py:82)
+}
+__global__ void p2t_tokens_kernel(const P2tTokParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long long)p.B * p.M) return;
+  const int tok = (int)(wid % p.M), b = (int)(wid / p.M);
+  int l = 0;
+  while (l + 1 < p.n_levels && tok >= p.off[l + 1]) ++l;
+  const int r = tok - p.off[l], pi = r / p.pw[l], pj = r - pi * p.pw[l];
+  const float* base = p.pooled + ((long long)b * p.M + p.off[l]) * p.C;     // this level's map of image b, [ph*pw, C]
+  float s = 0.f;
+  for (int c = lane; c < p.C; c += 32) s += p2t_token_value(p, base, l, pi, pj, c);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / p.C;
+  float v = 0.f;
+  for (int c = lane; c < p.C; c += 32) { const float d = p2t_token_value(p, base, l, pi, pj, c) - mean; v = fmaf(d, d, v); }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = rsqrtf(v / p.C + p.eps);
+  __half* orow = reinterpret_cast<__half*>(p.out) + ((long long)b * p.M + tok) * p.C;
+  for (int c = lane; c < p.C; c += 32)
+    orow[c] = __float2half_rn(fmaf((p2t_token_value(p, base, l, pi, pj, c) - mean) * rstd, __ldg(p.gamma + c), __ldg(p.beta + c)));
+}
+
 // SegFormer spatial reduction (segformer.py:27, 38-39): a DENSE conv with k = stride = sr is a GEMM over non-overlapping
 // patches.  This kernel lays the patches out as that GEMM's K-major A operand -- a pure re-partition of x (kernel == stride:
 // every element of x moves exactly once):  out[b, i*Ws+j, (u*sr+v)*C + c] = x[b, (sr*i+u)*W + sr*j+v, c]

@@ -81,6 +81,10 @@ ORACLE_CASES = {
     "cmt_s_stage4": dict(variant="cmt", ctor=dict(dim=512, num_heads=8, sr_ratio=1), x=(2, 49, 512), hw=(7, 7)),
     # 240 keys after the reduction: the widest S tile of the single-slot kernel, both column halves carry the bias
     "cmt_240keys": dict(variant="cmt", ctor=dict(dim=128, num_heads=2, sr_ratio=1), x=(1, 240, 128), hw=(12, 20)),
+    # P2T zoo stages (p2t.py: embed_dims 64/128/320/512, heads 1/2/5/8, pool ratios 12/16/20/24 at 56x56 ... 1/2/3/4 at 7x7)
+    "p2t_stage1": dict(variant="p2t", ctor=dict(dim=64, num_heads=1, qkv_bias=True, pool_ratios=[12, 16, 20, 24]), x=(1, 3136, 64), hw=(56, 56)),
+    "p2t_stage3": dict(variant="p2t", ctor=dict(dim=320, num_heads=5, qkv_bias=True, pool_ratios=[3, 4, 5, 6]), x=(2, 196, 320), hw=(14, 14)),
+    "p2t_stage4": dict(variant="p2t", ctor=dict(dim=512, num_heads=8, qkv_bias=True, pool_ratios=[1, 2, 3, 4]), x=(2, 49, 512), hw=(7, 7)),
     # block attention halves (row f-1): PVT C3 geometry, a dense-reduction block is covered through pvt.Block's entry point
     "pvtblock_c3_b2": dict(variant="pvt_block", ctor=dict(dim=512, num_heads=8, sr_ratio=8), x=(2, 4096, 512), hw=(64, 64)),
     "pvtblock_sr1_bias": dict(variant="pvt_block", ctor=dict(dim=128, num_heads=2, sr_ratio=1, qkv_bias=True), x=(2, 196, 128), hw=(14, 14)),

@@ -196,3 +196,27 @@ def test_pam_matches_live_reference_contract():
     r, m = ref(64), pa.dual_attention.PAM(64)
     assert {k: v.shape for k, v in r.state_dict().items()} == {k: v.shape for k, v in m.state_dict().items()}
     m.load_state_dict(r.state_dict())
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
+def test_dilateformer_global_attention_matches_live_reference_contract():
+    from oracle.cases import load_reference_class
+    ref = load_reference_class(REF, "dilateformer", "GlobalAttention")
+    ours = pa.dilateformer.GlobalAttention
+    assert str(inspect.signature(ref.__init__)) == str(inspect.signature(ours.__init__))
+    r, m = ref(128, 2, qkv_bias=True), ours(128, 2, qkv_bias=True)
+    assert {k: v.shape for k, v in r.state_dict().items()} == {k: v.shape for k, v in m.state_dict().items()}
+    m.load_state_dict(r.state_dict())
+    assert ours(128, 2, qk_scale=0.25).scale == ref(128, 2, qk_scale=0.25).scale == 0.25
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
+def test_p2t_pooling_attention_matches_live_reference_contract():
+    ref = _ref("p2t").PoolingAttention
+    ours = pa.p2t.PoolingAttention
+    assert str(inspect.signature(ref.__init__)) == str(inspect.signature(ours.__init__))
+    assert str(inspect.signature(ref.forward)) == str(inspect.signature(ours.forward))
+    r, m = ref(128, 2, qkv_bias=True), ours(128, 2, qkv_bias=True)
+    assert {k: v.shape for k, v in r.state_dict().items()} == {k: v.shape for k, v in m.state_dict().items()}
+    m.load_state_dict(r.state_dict())
+    assert m.num_elements == r.num_elements
