@@ -74,6 +74,7 @@ struct CsParams {
   void* d[2];              // their outputs, row-major [M, N] 16-bit (contiguous rows)
   int K;
   int lag;                 // tile order: the proj tiles of m-group j follow the qkv tiles of m-group j + lag (see cs_tile)
+  int tail;                // the proj tiles of the LAST `tail` m-groups are cut into 256 x 64 quarters (see cs_tile); lag == m_groups only
   AttnParams at;
   int* sched;
   long long* trace;        // debug: per CTA {role, worker, start, first unit ready, end} on the global timer, or nullptr
@@ -108,27 +109,41 @@ __device__ __forceinline__ void cs_regs_worker() { asm volatile("setmaxnreg.inc.
 // behind it in its worker.  The order is deadlock-free for any lag >= 1: a proj tile waits
 // for attention units that need only qkv tiles of m-groups <= its own + 1, all EARLIER in this order, and qkv tiles wait for
 // nothing -- by induction over the order every tile's dependencies complete.
-struct CsTile { int ph, mg, nt; };
+// Tail split: the kernel ends with the proj tiles of the last images, which cannot start before the attention stream has
+// finished them -- a handful of 256 x 256 tiles (11-13 k cycles each) on a handful of workers while the other seventy idle.
+// Those tiles (the last `tail` m-groups of the proj phase) are issued as 256 x 64 quarters instead: four times as many
+// workers share the tail, each for a third of the time (a 64-wide tile is shared-memory-port-bound, ~310 cycles per k-block
+// against 512 for the full width -- irrelevant when the alternative is idling).
+struct CsTile { int ph, mg, col0, bn; };
 __device__ __forceinline__ CsTile cs_tile(const CsParams& P, int t) {
   const int n1 = P.g[0].n_tiles, n2 = P.g[1].n_tiles, MG = P.g[0].m_groups, D = P.lag;
   CsTile r;
-  if (t < D * n1) { r.ph = 0; r.mg = t / n1; r.nt = t - r.mg * n1; return r; }
+  r.bn = CS_BN;
+  if (t < D * n1) { r.ph = 0; r.mg = t / n1; r.col0 = (t - r.mg * n1) * CS_BN; return r; }
   t -= D * n1;
   const int per = n1 + n2, s = t / per;
   if (s < MG - D) {
     const int q = t - s * per;
-    if (q < n1) { r.ph = 0; r.mg = D + s; r.nt = q; }
-    else { r.ph = 1; r.mg = s; r.nt = q - n1; }
+    if (q < n1) { r.ph = 0; r.mg = D + s; r.col0 = q * CS_BN; }
+    else { r.ph = 1; r.mg = s; r.col0 = (q - n1) * CS_BN; }
     return r;
   }
   t -= (MG - D) * per;
-  r.ph = 1; r.mg = MG - D + t / n2; r.nt = t % n2;
+  r.ph = 1;
+  const int full = (D - P.tail) * n2;            // proj tiles of full width (tail > 0 only with D == MG)
+  if (t < full) { r.mg = MG - D + t / n2; r.col0 = (t % n2) * CS_BN; return r; }
+  t -= full;
+  const int nq = n2 * (CS_BN / 64);
+  r.mg = MG - P.tail + t / nq;
+  r.col0 = (t % nq) * 64;
+  r.bn = 64;
   return r;
 }
 
 // ================================================================================================ role G
 __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUtensorMap& tmB1, const CUtensorMap& tmD1,
                                              const CUtensorMap& tmA2, const CUtensorMap& tmB2, const CUtensorMap& tmD2,
+                                             const CUtensorMap& tmB2q,
                                              const CsParams& P, uint8_t* smem, uint64_t* bars, uint32_t tmem_base,
                                              int worker, int nworkers, int crank) {
   uint64_t* full_bar = bars;                 // [3] leader's: both CTAs' TMA bytes
@@ -148,11 +163,12 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
     uint32_t phase = 0;
     for (int t = worker; t < T; t += nworkers, ++tseq) {
       const CsTile tl = cs_tile(P, t);
-      const int ph = tl.ph, mg = tl.mg, nt = tl.nt;
+      const int ph = tl.ph, mg = tl.mg;
       const CsGemmPhase& g = P.g[ph];
       const int mt = mg * 2 + crank;
       const CUtensorMap* tA = ph ? &tmA2 : &tmA1;
-      const CUtensorMap* tB = ph ? &tmB2 : &tmB1;
+      const CUtensorMap* tB = tl.bn == 64 ? &tmB2q : ph ? &tmB2 : &tmB1;      // quarter tiles: 32 B rows per CTA
+      const uint32_t stage_tx = 2 * (16384 + (uint32_t)(tl.bn / 2) * 128);    // both CTAs: A 128 x 64 + B (bn / 2) x 64
       if (g.wait_ctr != nullptr) {
         if (elect_one()) {
           const int r0 = mt * GEMM_BLOCK_M, r1 = min(r0 + GEMM_BLOCK_M, g.M) - 1;
@@ -166,9 +182,9 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
         uint8_t* sa = smem + stage * CS_STAGE_BYTES;
         if (elect_one()) {
           if (kb == 0) CS_TRACE_G(tseq, 0);
-          if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * CS_STAGE_BYTES);
+          if (crank == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
           tma_load_3d_2sm(sa, tA, kb * GEMM_BLOCK_K, mt * GEMM_BLOCK_M, 0, &full_bar[stage]);
-          tma_load_3d_2sm(sa + 16384, tB, kb * GEMM_BLOCK_K, nt * CS_BN + crank * (CS_BN / 2), 0, &full_bar[stage]);
+          tma_load_3d_2sm(sa + 16384, tB, kb * GEMM_BLOCK_K, tl.col0 + crank * (tl.bn / 2), 0, &full_bar[stage]);
         }
         __syncwarp();
         if (++stage == CS_STAGES) { stage = 0; phase ^= 1; }
@@ -181,7 +197,9 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
       uint32_t phase = 0, acc_phase = 0;
       const uint32_t smem_base = smem_u32(smem);
       for (int t = worker; t < T; t += nworkers, ++tseq) {
-        const uint32_t idesc = P.g[cs_tile(P, t).ph].idesc;
+        const CsTile tlm = cs_tile(P, t);
+        const uint32_t idesc = tlm.bn == CS_BN ? P.g[tlm.ph].idesc
+                                               : (P.g[tlm.ph].idesc & ~(0x3Fu << 17)) | ((uint32_t)(tlm.bn >> 3) << 17);
         mbar_wait(tempty_bar, acc_phase ^ 1);           // single accumulator: drained by both CTAs' epilogue warps
         acc_phase ^= 1;
         tc_fence_after();
@@ -218,7 +236,8 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
     const bool tracer = (warp == 4 && lane == 0);
     for (int t = worker; t < T; t += nworkers, ++tseq) {
       const CsTile tl = cs_tile(P, t);
-      const int ph = tl.ph, mg = tl.mg, nt = tl.nt;
+      const int ph = tl.ph, mg = tl.mg;
+      const int nchunks = tl.bn / 64;                 // 32-column chunks of this warp: 4 (full tile) or 1 (quarter tile)
       const CsGemmPhase& g = P.g[ph];
       const int mt = mg * 2 + crank;
       const int row0 = mt * GEMM_BLOCK_M + q * 32;
@@ -235,18 +254,18 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
       const bool rows_ok = row0 < g.M;
       const bool has_bias = g.bias != nullptr;
       float4 bq[8];
-      if (has_bias && nt * CS_BN + half * 32 < g.N) {
+      if (has_bias && tl.col0 + half * 32 < g.N) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(g.bias + nt * CS_BN + half * 32) + i);
+        for (int i = 0; i < 8; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(g.bias + tl.col0 + half * 32) + i);
       }
 #pragma unroll 1
-      for (int j = 0; j < CS_BN / 64; ++j) {
+      for (int j = 0; j < nchunks; ++j) {
         const int c = half * 32 + j * 64;
-        const int col = nt * CS_BN + c;
+        const int col = tl.col0 + c;
         uint32_t v[32];
         tmem_ld32(t_base + c, v);
         tmem_ld_wait();
-        if (j == CS_BN / 64 - 1) {
+        if (j == nchunks - 1) {
           // this warp's last TMEM read of the tile: hand the accumulator back before converting the chunk
           tc_fence_before();
           __syncwarp();
@@ -262,7 +281,7 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
               v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + bq[i].z);
               v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + bq[i].w);
             }
-            if (j + 1 < CS_BN / 64 && col + 64 < g.N) {
+            if (j + 1 < nchunks && col + 64 < g.N) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(g.bias + col + 64) + i);
             }
@@ -639,7 +658,7 @@ vit_cosched_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2,
                    const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD2,
-                   const CsParams P) {
+                   const __grid_constant__ CUtensorMap tmB2q, const CsParams P) {
   extern __shared__ uint8_t cs_raw[];
   const uint32_t pad = (1024u - (smem_u32(cs_raw) & 1023u)) & 1023u;
   uint8_t* smem = cs_raw + pad;
@@ -686,7 +705,7 @@ vit_cosched_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   if (warp == 0 && lane == 0) {
     if (role == 0) {
       tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); tma_prefetch_desc(&tmD1);
-      tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); tma_prefetch_desc(&tmD2);
+      tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); tma_prefetch_desc(&tmD2); tma_prefetch_desc(&tmB2q);
     } else {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
     }
@@ -734,7 +753,7 @@ vit_cosched_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
       }
     }
   } else if (role == 0) {
-    if (!(P.debug & 2)) cs_gemm_role(tmA1, tmB1, tmD1, tmA2, tmB2, tmD2, P, smem, bars, tmem_base, cworker, nclusters_role, crank);
+    if (!(P.debug & 2)) cs_gemm_role(tmA1, tmB1, tmD1, tmA2, tmB2, tmD2, tmB2q, P, smem, bars, tmem_base, cworker, nclusters_role, crank);
   } else {
     if (!(P.debug & 1)) cs_attn_role<false>(tmQ, tmK, tmV, tmO, P, smem, bars, tmem_base, cworker * 2 + crank, nclusters_role * 2);
   }
