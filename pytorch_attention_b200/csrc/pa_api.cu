@@ -42,6 +42,7 @@ struct EnvCfg {
   int vit_cosched = -1;      // -1 unset (co-scheduled kernel when it qualifies), 0 never, 1 required
   int fused_bn1 = 0, fused_bn2 = 0;
   int cs_debug = 0, cs_lag = 0, gemm_one_set = 0, attn_two_slot = 0, cswin_two_kernels = 0;
+  int cs_qtail = -1;         // the same for the last m-groups of the qkv phase
   int cs_tail = -1;          // co-scheduled kernel: m-groups at the end of the proj phase issued as 256 x 64 quarters (-1: default)
   int pvt_fused = 0;         // 1: attention core + proj GEMM as ONE kernel (pa_attn_proj.cuh; measured slower, see there)
 };
@@ -73,6 +74,7 @@ const EnvCfg* env_load() {
   c->cswin_two_kernels = getenv("PA_CSWIN_TWO_KERNELS") != nullptr;
   c->pvt_fused = env_int("PA_PVT_FUSED", 0);
   c->cs_tail = env_int("PA_CS_TAIL", -1);
+  c->cs_qtail = env_int("PA_CS_QTAIL", -1);
   return c;
 }
 inline const EnvCfg& env() {
@@ -694,7 +696,7 @@ static int launch_vit_fused(const GemmPlan& p1, const AttnPlan& pa_, const GemmP
 // (no work: every CTA allocates its TMEM, announces itself and waits up to ~5 ms to see the whole grid) -- one launch and
 // one stream synchronisation at the first qualifying call; never inside a stream capture (that call takes the other path).
 static int launch_vit_cosched(const GemmPlan& p1, const CUtensorMap& tmD1, const AttnPlan& pa_, const GemmPlan& p2, const CUtensorMap& tmD2,
-                              const CUtensorMap& tmB2q, CsParams cp, int smem, cudaStream_t st) {
+                              const CUtensorMap& tmB1q, const CUtensorMap& tmB2q, CsParams cp, int smem, cudaStream_t st) {
   struct DevState { int smem_set = 0; int probed_smem = 0; int resident = 0; };
   static DevState state[64];
   static std::mutex mu;
@@ -727,7 +729,7 @@ static int launch_vit_cosched(const GemmPlan& p1, const CUtensorMap& tmD1, const
       CsParams pp = cp;
       pp.probe = cp.sched + cs_sched_ints(grid);
       PA_CUDA_OK(cudaMemsetAsync(pp.probe, 0, 2 * sizeof(int), st));
-      PA_CUDA_OK(cudaLaunchKernelEx(&cfg, vit_cosched_kernel, p1.tmA, p1.tmB, tmD1, pa_.tq, pa_.tk, pa_.tv, pa_.to, p2.tmA, p2.tmB, tmD2, tmB2q, pp));
+      PA_CUDA_OK(cudaLaunchKernelEx(&cfg, vit_cosched_kernel, p1.tmA, p1.tmB, tmD1, pa_.tq, pa_.tk, pa_.tv, pa_.to, p2.tmA, p2.tmB, tmD2, tmB1q, tmB2q, pp));
       int seen[2] = {0, 0};
       PA_CUDA_OK(cudaMemcpyAsync(seen, pp.probe, sizeof(seen), cudaMemcpyDeviceToHost, st));
       PA_CUDA_OK(cudaStreamSynchronize(st));
@@ -742,7 +744,7 @@ static int launch_vit_cosched(const GemmPlan& p1, const CUtensorMap& tmD1, const
     }
   }
   cp.probe = nullptr;
-  PA_CUDA_OK(cudaLaunchKernelEx(&cfg, vit_cosched_kernel, p1.tmA, p1.tmB, tmD1, pa_.tq, pa_.tk, pa_.tv, pa_.to, p2.tmA, p2.tmB, tmD2, tmB2q, cp));
+  PA_CUDA_OK(cudaLaunchKernelEx(&cfg, vit_cosched_kernel, p1.tmA, p1.tmB, tmD1, pa_.tq, pa_.tk, pa_.tv, pa_.to, p2.tmA, p2.tmB, tmD2, tmB1q, tmB2q, cp));
   return PA_OK;
 }
 
@@ -937,12 +939,15 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
           cp.lag = lag < 1 ? 1 : lag > MG ? MG : lag;
         }
         // tail split (cs_tile): the proj tiles of the last m-groups as 256 x 64 quarters; their B boxes hold 32 rows per CTA
-        CUtensorMap tmB2q;
+        CUtensorMap tmB1q, tmB2q;
         {
           uint64_t dims[3] = {(uint64_t)C, (uint64_t)C, 1};
           uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)C * C * 2};
           uint32_t box[3] = {64, 32, 1};
           if ((rc = make_tmap_16b(&tmB2q, PA_DTYPE_F16, a->proj_weight, 3, dims, str, box))) return rc;
+          uint64_t dims1[3] = {(uint64_t)C, (uint64_t)(3 * C), 1};
+          uint64_t str1[2] = {(uint64_t)C * 2, (uint64_t)C * 3 * C * 2};
+          if ((rc = make_tmap_16b(&tmB1q, a->dtype, a->qkv_weight, 3, dims1, str1, box))) return rc;
         }
         {
           const int MG = cp.g[0].m_groups;
@@ -954,11 +959,16 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
           if (tail > MG) tail = MG;
           cp.tail = tail;
           cp.g[1].tiles = (MG - tail) * cp.g[1].n_tiles + tail * cp.g[1].n_tiles * (CS_BN / 64);
+          int qtail = ev.cs_qtail >= 0 ? ev.cs_qtail : 0;
+          if (cp.lag != MG) qtail = 0;
+          if (qtail > MG) qtail = MG;
+          cp.qtail = qtail;
+          cp.g[0].tiles = (MG - qtail) * cp.g[0].n_tiles + qtail * cp.g[0].n_tiles * (CS_BN / 64);
         }
         cp.d[0] = qkv; cp.d[1] = a->y;
         cp.at = pa_.p;
         cp.g[0].signal_ctr = counters;                       // per 128-row tile of qkv: every epilogue warp of every column tile
-        cp.at.wait_ctr = counters; cp.at.wait_target = cp.g[0].n_tiles * CS_EPI_WARPS;
+        cp.at.wait_ctr = counters; cp.at.wait_target = cp.g[0].n_tiles * CS_EPI_WARPS * (CS_BN / 64);   // a full tile's warp publishes 4, a quarter's 1
         cp.at.wait_rows_per_group = a->N;
         cp.at.signal_ctr = counters + n_mt;                  // per image: one count per (head, query tile)
         cp.g[1].wait_ctr = counters + n_mt; cp.g[1].wait_rows = a->N; cp.g[1].wait_target = a->H * cp.at.q_tiles;
@@ -968,7 +978,7 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
         if (cp.debug & 1) cp.g[1].wait_ctr = nullptr;       // experiments: the idle role's dependants must not wait for it
         if (cp.debug & 2) cp.at.wait_ctr = nullptr;
         PA_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)(n_mt + a->B + cs_sched_ints(grid_cs)) * sizeof(int), st));
-        rc = launch_vit_cosched(p1, tmD1, pa_, p2, tmD2, tmB2q, cp, cs_smem_bytes(pa_.p.kb) + 1024, st);
+        rc = launch_vit_cosched(p1, tmD1, pa_, p2, tmD2, tmB1q, tmB2q, cp, cs_smem_bytes(pa_.p.kb) + 1024, st);
         if (rc < 0) return rc;
         if (rc == 0) { launch_counter()++; t_last_vit_path = 3; return PA_OK; }
         if (ev.vit_cosched > 0) return PA_ERR_UNSUPPORTED;    // message set by launch_vit_cosched

@@ -75,6 +75,7 @@ struct CsParams {
   int K;
   int lag;                 // tile order: the proj tiles of m-group j follow the qkv tiles of m-group j + lag (see cs_tile)
   int tail;                // the proj tiles of the LAST `tail` m-groups are cut into 256 x 64 quarters (see cs_tile); lag == m_groups only
+  int qtail;               // the same for the last `qtail` m-groups of the qkv phase
   AttnParams at;
   int* sched;
   long long* trace;        // debug: per CTA {role, worker, start, first unit ready, end} on the global timer, or nullptr
@@ -114,11 +115,35 @@ __device__ __forceinline__ void cs_regs_worker() { asm volatile("setmaxnreg.inc.
 // Those tiles (the last `tail` m-groups of the proj phase) are issued as 256 x 64 quarters instead: four times as many
 // workers share the tail, each for a third of the time (a 64-wide tile is shared-memory-port-bound, ~310 cycles per k-block
 // against 512 for the full width -- irrelevant when the alternative is idling).
+// The qkv phase has the same problem one dependency earlier: 450 tiles on 74 workers are 6 rounds + 6 tiles, the attention of the
+// last image cannot start before that seventh round has finished, and everything behind it (its attention units, their proj
+// tiles) sits on the kernel's critical path.  `qtail`: the LAST m-groups of the qkv phase as quarters as well (the counters a
+// quarter publishes weigh 1, a full tile's 4, so the attention role's target is the same for every m-tile).
 struct CsTile { int ph, mg, col0, bn; };
 __device__ __forceinline__ CsTile cs_tile(const CsParams& P, int t) {
   const int n1 = P.g[0].n_tiles, n2 = P.g[1].n_tiles, MG = P.g[0].m_groups, D = P.lag;
+  constexpr int QPT = CS_BN / 64;                // quarters per tile
   CsTile r;
   r.bn = CS_BN;
+  if (D == MG) {
+    // [qkv full][qkv quarters][proj full][proj quarters]
+    r.ph = 0;
+    const int full1 = (MG - P.qtail) * n1;
+    if (t < full1) { r.mg = t / n1; r.col0 = (t - r.mg * n1) * CS_BN; return r; }
+    t -= full1;
+    const int nq1 = n1 * QPT;
+    if (t < P.qtail * nq1) { r.mg = MG - P.qtail + t / nq1; r.col0 = (t % nq1) * 64; r.bn = 64; return r; }
+    t -= P.qtail * nq1;
+    r.ph = 1;
+    const int full2 = (MG - P.tail) * n2;
+    if (t < full2) { r.mg = t / n2; r.col0 = (t % n2) * CS_BN; return r; }
+    t -= full2;
+    const int nq2 = n2 * QPT;
+    r.mg = MG - P.tail + t / nq2;
+    r.col0 = (t % nq2) * 64;
+    r.bn = 64;
+    return r;
+  }
   if (t < D * n1) { r.ph = 0; r.mg = t / n1; r.col0 = (t - r.mg * n1) * CS_BN; return r; }
   t -= D * n1;
   const int per = n1 + n2, s = t / per;
@@ -129,21 +154,14 @@ __device__ __forceinline__ CsTile cs_tile(const CsParams& P, int t) {
     return r;
   }
   t -= (MG - D) * per;
-  r.ph = 1;
-  const int full = (D - P.tail) * n2;            // proj tiles of full width (tail > 0 only with D == MG)
-  if (t < full) { r.mg = MG - D + t / n2; r.col0 = (t % n2) * CS_BN; return r; }
-  t -= full;
-  const int nq = n2 * (CS_BN / 64);
-  r.mg = MG - P.tail + t / nq;
-  r.col0 = (t % nq) * 64;
-  r.bn = 64;
+  r.ph = 1; r.mg = MG - D + t / n2; r.col0 = (t % n2) * CS_BN;
   return r;
 }
 
 // ================================================================================================ role G
 __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUtensorMap& tmB1, const CUtensorMap& tmD1,
                                              const CUtensorMap& tmA2, const CUtensorMap& tmB2, const CUtensorMap& tmD2,
-                                             const CUtensorMap& tmB2q,
+                                             const CUtensorMap& tmB1q, const CUtensorMap& tmB2q,
                                              const CsParams& P, uint8_t* smem, uint64_t* bars, uint32_t tmem_base,
                                              int worker, int nworkers, int crank) {
   uint64_t* full_bar = bars;                 // [3] leader's: both CTAs' TMA bytes
@@ -167,7 +185,7 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
       const CsGemmPhase& g = P.g[ph];
       const int mt = mg * 2 + crank;
       const CUtensorMap* tA = ph ? &tmA2 : &tmA1;
-      const CUtensorMap* tB = tl.bn == 64 ? &tmB2q : ph ? &tmB2 : &tmB1;      // quarter tiles: 32 B rows per CTA
+      const CUtensorMap* tB = tl.bn == 64 ? (ph ? &tmB2q : &tmB1q) : ph ? &tmB2 : &tmB1;      // quarter tiles: 32 B rows per CTA
       const uint32_t stage_tx = 2 * (16384 + (uint32_t)(tl.bn / 2) * 128);    // both CTAs: A 128 x 64 + B (bn / 2) x 64
       if (g.wait_ctr != nullptr) {
         if (elect_one()) {
@@ -250,7 +268,9 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
       // store.  With two CTAs of 113 KB on the SM there is no L1 left: the column biases come from L2, so the 8 x 16-byte
       // bias loads of chunk j+1 are issued while chunk j is converted and staged (measured: biased tiles drained in 4.6 k
       // cycles with the loads in line, unbiased ones in 3.0 k).  Measured and rejected: the TMEM load of chunk j+1 in flight
-      // during chunk j (no gain), rows stored straight from registers (drain 2.9 k -> 5.5 k cycles).
+      // during chunk j (no gain), rows stored straight from registers (drain 2.9 k -> 5.5 k cycles); late round 2: all four chunks
+      // held as packed registers and staged under the next mainloop (accumulator free 1.5 k cycles earlier, mainloop 0.7 k longer:
+      // 87.2 vs 86.2 us, and again 86.7 vs 85.0 us on top of the tail split) -- profiles/cosched_drain_variants_r02.txt.
       const bool rows_ok = row0 < g.M;
       const bool has_bias = g.bias != nullptr;
       float4 bq[8];
@@ -311,7 +331,7 @@ __device__ __forceinline__ void cs_gemm_role(const CUtensorMap& tmA1, const CUte
       }
       if (tracer) CS_TRACE_G(tseq, 6);
       // publish right away: with a single accumulator this warp has nothing to do until the next mainloop has finished
-      if (lane == 0 && g.signal_ctr != nullptr && mt < g.m_tiles) signal_counter(g.signal_ctr + mt);
+      if (lane == 0 && g.signal_ctr != nullptr && mt < g.m_tiles) signal_counter(g.signal_ctr + mt, tl.bn == CS_BN ? CS_BN / 64 : 1);
       if (tracer) CS_TRACE_G(tseq, 7);
       __syncwarp();
     }
@@ -658,7 +678,7 @@ vit_cosched_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2,
                    const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD2,
-                   const __grid_constant__ CUtensorMap tmB2q, const CsParams P) {
+                   const __grid_constant__ CUtensorMap tmB1q, const __grid_constant__ CUtensorMap tmB2q, const CsParams P) {
   extern __shared__ uint8_t cs_raw[];
   const uint32_t pad = (1024u - (smem_u32(cs_raw) & 1023u)) & 1023u;
   uint8_t* smem = cs_raw + pad;
@@ -705,7 +725,7 @@ vit_cosched_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   if (warp == 0 && lane == 0) {
     if (role == 0) {
       tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); tma_prefetch_desc(&tmD1);
-      tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); tma_prefetch_desc(&tmD2); tma_prefetch_desc(&tmB2q);
+      tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); tma_prefetch_desc(&tmD2); tma_prefetch_desc(&tmB1q); tma_prefetch_desc(&tmB2q);
     } else {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
     }
@@ -753,7 +773,7 @@ vit_cosched_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
       }
     }
   } else if (role == 0) {
-    if (!(P.debug & 2)) cs_gemm_role(tmA1, tmB1, tmD1, tmA2, tmB2, tmD2, tmB2q, P, smem, bars, tmem_base, cworker, nclusters_role, crank);
+    if (!(P.debug & 2)) cs_gemm_role(tmA1, tmB1, tmD1, tmA2, tmB2, tmD2, tmB1q, tmB2q, P, smem, bars, tmem_base, cworker, nclusters_role, crank);
   } else {
     if (!(P.debug & 1)) cs_attn_role<false>(tmQ, tmK, tmV, tmO, P, smem, bars, tmem_base, cworker * 2 + crank, nclusters_role * 2);
   }

@@ -314,10 +314,10 @@ __device__ __forceinline__ void wait_counter_ge(const int* ctr, int target) {
   asm volatile("fence.proxy.async;" ::: "memory");
 }
 // publish: all bulk stores of this thread are complete -> release the counter
-__device__ __forceinline__ void signal_counter(int* ctr) {
+__device__ __forceinline__ void signal_counter(int* ctr, int weight = 1) {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __threadfence();
-  atomicAdd(ctr, 1);
+  atomicAdd(ctr, weight);
 }
 
 // ---------------------------------------------------------------- descriptors

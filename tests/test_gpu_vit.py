@@ -308,3 +308,25 @@ def test_vit_block_attention_half_fused_prenorm_and_residual():
         cpu = blk.float().cpu()
         want = ref + cpu.mlp(cpu.layernorm2(ref))
     assert full.dtype == torch.float32 and rel_fro(full.cpu(), want) < 2e-3
+
+
+@pytest.mark.parametrize("B,C,H,N", [(64, 768, 12, 197), (9, 256, 4, 130), (16, 1024, 16, 197)])
+@pytest.mark.parametrize("tail,qtail,debug", [(0, 0, 0), (4, 0, 0), (1, 1, 0), (4, 2, 0), (50, 50, 0)])
+def test_cosched_tail_splits_are_bit_equal(B, C, H, N, tail, qtail, debug, monkeypatch):
+    """PA_CS_TAIL / PA_CS_QTAIL issue the proj / qkv tiles of the last m-groups as 256 x 64 quarter tiles (weighted dependency
+    counters): scheduling only -- every variant must reproduce the three-launch
+    output bit for bit (50 > number of m-groups where B is small: every tile a quarter)."""
+    m, x = _fresh(C, H, B, N, 5)
+    m = m.cuda()
+    xg = x.cuda()
+    try:
+        with torch.no_grad():
+            _setenv(monkeypatch, PA_VIT_FUSED=0, PA_VIT_COSCHED=0)
+            y3 = m(xg)
+            _setenv(monkeypatch, PA_VIT_FUSED=None, PA_VIT_COSCHED=1, PA_CS_TAIL=tail, PA_CS_QTAIL=qtail, PA_CS_DEBUG=debug)
+            yc = m(xg)
+            for _ in range(3):
+                assert torch.equal(m(xg), yc)
+            assert torch.equal(yc, y3)
+    finally:
+        _setenv(monkeypatch, PA_VIT_FUSED=None, PA_VIT_COSCHED=None, PA_CS_TAIL=None, PA_CS_QTAIL=None, PA_CS_DEBUG=None)
