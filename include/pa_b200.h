@@ -105,6 +105,10 @@ typedef struct {
   const void* proj_weight;   /* [C,C] fp16 */
   const float* proj_bias;    /* [C] fp32 or NULL */
   void* y;                   /* [B,N,C] */
+  int topk;                  /* 0: plain softmax.  > 0: kvt.KNNAttention (kvt.py:67-94): only the topk largest
+                                scores of every row take part in the softmax (kvt.py:84-87).  Needs 64-wide heads, N <= 240 and
+                                topk <= N; runs as GEMM(qkv) -> per-row k-th-largest kernel -> attention core (scores below the row's
+                                threshold masked) -> GEMM(proj) */
 } pa_vit_args;
 /* One kernel launch when N <= 256, three stream-ordered launches otherwise; all paths give bit-identical results.
  *   co-scheduled kernel (default when N <= 240, C % 64 == 0, 16-bit y): two role-specialised CTAs per SM -- the qkv / proj

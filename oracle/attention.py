@@ -62,6 +62,31 @@ def vit_attention(x, qkv_weight, qkv_bias, proj_weight, proj_bias, num_heads, sc
     return _lin(o, proj_weight, proj_bias)                      # ViT.py:87
 
 
+def kvt_knn_attention(x, qkv_weight, qkv_bias, proj_weight, proj_bias, num_heads, topk, store_dtype=None):
+    """kvt.KNNAttention.forward (kvt.py:79-94): ViT's attention in which only the topk largest scaled scores of every row take
+    part in the softmax -- the rest are -inf (mask built by torch.topk + scatter, kvt.py:84-87).
+
+    The top-k SELECTION is discontinuous: rounding q / k to 16 bits moves scores by ~5e-4 relative, which swaps the k-th and
+    (k+1)-th entry of a few per cent of the rows and changes those rows by ~1/k of their mass (measured on the golden cases: 1.5 %
+    of the rows, rel-Frobenius 6e-3 at k = 100 of 197; 4e-2 at k = 7 of 50) -- no 16-bit implementation can meet 1e-3 against the
+    fp32 forward.  ``store_dtype=torch.float16`` rounds the qkv projection the way the B200 path stores it, so that both sides
+    select on the same scores; tests compare against that, and against the fp32 reference row by row."""
+    B, N, C = x.shape
+    H = num_heads
+    hd = C // H
+    qkv = _lin(x, qkv_weight, qkv_bias)
+    if store_dtype is not None:
+        qkv = qkv.to(store_dtype).to(x.dtype)
+    qkv = qkv.reshape(B, N, 3, H, hd)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    s = torch.einsum("bnhd,bmhd->bhnm", q, k) * hd ** -0.5
+    kth = torch.sort(s, dim=-1, descending=True).values[..., topk - 1:topk]      # the k-th largest score of every row
+    s = torch.where(s >= kth, s, torch.full_like(s, float("-inf")))
+    p = _softmax_last(s)
+    o = torch.einsum("bhnm,bmhd->bnhd", p, v).reshape(B, N, C)
+    return _lin(o, proj_weight, proj_bias)
+
+
 def bvit_broad_attention(x, to_qkv_weight, to_out_weight, to_out_bias, heads, dim_head):
     """bvit.Broad_Attention.forward (bvit.py:66-76): returns (out, q, k, v) with q, k, v as [B, heads, N, dim_head].
     Inner width heads * dim_head; to_qkv has no bias; without an output projection (to_out = Identity, bvit.py:52) out is the

@@ -31,6 +31,9 @@ GOLDEN_CASES = {
     # p2t.PoolingAttention(dim, num_heads, pool_ratios).forward(x, H, W, d_convs): keys / values from a pooling pyramid   p2t.py:46-94
     "p2t_b2_14x14_c128_h2": dict(variant="p2t", ctor=dict(dim=128, num_heads=2, qkv_bias=True, pool_ratios=[1, 2, 3, 6]), x=(2, 196, 128), hw=(14, 14)),
     "p2t_b2_12x20_c64_h1_ratios_3_4_5": dict(variant="p2t", ctor=dict(dim=64, num_heads=1, pool_ratios=[3, 4, 5]), x=(2, 240, 64), hw=(12, 20)),
+    # kvt.KNNAttention(dim, num_heads, topk): only the topk largest scores of a row enter the softmax      kvt.py:67-94
+    "kvt_b2_n197_c128_h2_top100": dict(variant="kvt", ctor=dict(dim=128, num_heads=2, qkv_bias=True, topk=100), x=(2, 197, 128)),
+    "kvt_b2_n50_c64_h1_top7": dict(variant="kvt", ctor=dict(dim=64, num_heads=1, topk=7), x=(2, 50, 64)),
     # pvt.Attention(dim, num_heads, sr_ratio)            pvt.py:52-91
     "pvt_b2_16x16_c128_h2_sr4": dict(variant="pvt", ctor=dict(dim=128, num_heads=2, sr_ratio=4), x=(2, 256, 128), hw=(16, 16)),
     "pvt_b2_8x8_c128_h2_sr1_bias": dict(variant="pvt", ctor=dict(dim=128, num_heads=2, sr_ratio=1, qkv_bias=True), x=(2, 64, 128), hw=(8, 8)),
@@ -72,6 +75,7 @@ _REF_CLASS = {
     "bvit": ("bvit", "Broad_Attention"),
     "dilateformer": ("dilateformer", "GlobalAttention"),
     "p2t": ("p2t", "PoolingAttention"),
+    "kvt": ("kvt", "KNNAttention"),
     "pvt": ("pvt", "Attention"),
     "pvt_block": ("pvt", "Block"),
     "segformer": ("segformer", "Attention"),
@@ -158,7 +162,7 @@ def p2t_d_convs(inputs, device="cpu"):
 def load_reference(ref_path):
     if ref_path not in sys.path:
         sys.path.insert(0, ref_path)
-    return {m: importlib.import_module(m) for m in ("ViT", "pvt", "cvt", "cswin", "xcit", "moat", "segformer", "cmt", "bvit", "p2t")}
+    return {m: importlib.import_module(m) for m in ("ViT", "pvt", "cvt", "cswin", "xcit", "moat", "segformer", "cmt", "bvit", "p2t", "kvt")}
 
 
 def load_reference_class(ref_path, module, cls):
@@ -280,6 +284,9 @@ def run_oracle_case(spec, inputs, params, dtype=torch.float32):
         scale = c.get("qk_scale") or None
         return A.vit_attention(x.reshape(B_, H_ * W_, C_), P["qkv.weight"], P.get("qkv.bias"), P["proj.weight"], P["proj.bias"],
                                c.get("num_heads", 8), scale).reshape(B_, H_, W_, C_)
+    if v == "kvt":
+        return A.kvt_knn_attention(x, P["qkv.weight"], P.get("qkv.bias"), P["proj.weight"], P["proj.bias"],
+                                   c.get("num_heads", 4), c.get("topk", 100))
     if v == "pam":
         return A.pam_attention(x, P["b.weight"], P["b.bias"], P["c.weight"], P["c.bias"], P["d.weight"], P["d.bias"], P["alpha"])
     if v == "bvit":

@@ -8,7 +8,7 @@ the reference's file names so that ``from pytorch_attention_b200.pvt import Atte
 ``from pvt import Attention``.
 """
 from . import _lib, ops  # noqa: F401
-from . import vit, pvt, cvt, cswin, xcit, setr, moat, segformer, cmt, bvit, dual_attention, dilateformer, p2t  # noqa: F401
+from . import vit, pvt, cvt, cswin, xcit, setr, moat, segformer, cmt, bvit, dual_attention, dilateformer, p2t, kvt  # noqa: F401
 from .vit import Attention as ViTAttention  # noqa: F401
 from .vit import TransformerEncoder as ViTTransformerEncoder  # noqa: F401
 from .pvt import Attention as PVTAttention  # noqa: F401
@@ -16,5 +16,5 @@ from .cvt import Attention as CvTAttention  # noqa: F401
 from .cswin import LePEAttention, CSWinBlock  # noqa: F401
 from .xcit import XCA, ClassAttention  # noqa: F401
 
-__all__ = ["ops", "vit", "pvt", "cvt", "cswin", "xcit", "setr", "moat", "segformer", "cmt", "bvit", "dual_attention", "dilateformer", "p2t", "ViTAttention", "ViTTransformerEncoder", "PVTAttention", "CvTAttention",
+__all__ = ["ops", "vit", "pvt", "cvt", "cswin", "xcit", "setr", "moat", "segformer", "cmt", "bvit", "dual_attention", "dilateformer", "p2t", "kvt", "ViTAttention", "ViTTransformerEncoder", "PVTAttention", "CvTAttention",
            "LePEAttention", "CSWinBlock", "XCA", "ClassAttention"]

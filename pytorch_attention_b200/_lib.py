@@ -37,7 +37,7 @@ class VitArgs(C.Structure):
     _fields_ = [("dtype", _i), ("out_dtype", _i), ("B", _i), ("N", _i), ("C", _i), ("H", _i),
                 ("scale", _f),
                 ("x", _vp), ("qkv_weight", _vp), ("qkv_bias", _vp), ("proj_weight", _vp), ("proj_bias", _vp),
-                ("y", _vp)]
+                ("y", _vp), ("topk", _i)]
 
 
 class VitBlockArgs(C.Structure):

@@ -310,6 +310,7 @@ struct AttnLaunch {
   int B, R, H_sp, W_sp;   // windowed: images, resolution, window shape
   int add_into_out;
   const float* rel_pos;   // additive score bias [H, n_q, n_k] fp32 before the softmax (cmt.py:100), or nullptr
+  const float* row_thresh;  // per-row threshold on the raw scores [G, H, n_q] (kvt.py:84-87), or nullptr
 };
 
 template <int HD, bool WIN>
@@ -350,7 +351,7 @@ int attn_prepare(const AttnLaunch& a, AttnPlan* plan) {
   p.O = a.o; p.ldo = a.ldo; p.o_group = a.o_group; p.o_col0 = a.o_col0;
   p.scale_log2e = a.scale * 1.4426950408889634f;
   p.add_into_out = a.add_into_out;
-  p.rel_pos = a.rel_pos; p.rel_mul = 1.f / a.scale;
+  p.rel_pos = a.rel_pos; p.rel_mul = 1.f / a.scale; p.row_thresh = a.row_thresh;
   p.trace = g_gemm_trace;
   p.debug_flags = env().attn_debug;
   if (!a.windowed) {
@@ -470,7 +471,7 @@ int launch_attn_single_slot(const AttnPlan& plan, cudaStream_t st);   // below (
 
 int attn_launch(const AttnLaunch& a, cudaStream_t st) {
   if (attn_wide_hd(a.hd)) {
-    if (a.rel_pos) return fail(PA_ERR_UNSUPPORTED, "attention core with relative_pos: needs 64-wide heads (got %d)", a.hd);
+    if (a.rel_pos || a.row_thresh) return fail(PA_ERR_UNSUPPORTED, "attention core with relative_pos / top-k: needs 64-wide heads (got %d)", a.hd);
     if (a.windowed) return fail(PA_ERR_UNSUPPORTED, "windowed attention: head_dim %d unsupported (32 or 64)", a.hd);
     if (!(a.scale > 0.f)) return fail(PA_ERR_UNSUPPORTED, "attention core: scale must be > 0");
     if (a.ldo % 8 || a.o_col0 % 8 || a.o_group % 8 || (reinterpret_cast<uintptr_t>(a.o) & 15))
@@ -493,10 +494,10 @@ int attn_launch(const AttnLaunch& a, cudaStream_t st) {
   int rc = attn_prepare(a, &plan);
   if (rc) return rc;
   const int hd = a.hd;
-  if (a.rel_pos) {
-    // the score bias exists in the single-slot kernel only: 64-wide heads, at most 240 keys
+  if (a.rel_pos || a.row_thresh) {
+    // the score bias / row threshold exist in the single-slot kernel only: 64-wide heads, at most 240 keys
     if (hd != 64 || a.windowed || plan.p.nkb != 1 || !plan.p.tma_store || plan.p.kb > 240)
-      return fail(PA_ERR_UNSUPPORTED, "attention core with relative_pos: needs 64-wide heads and at most 240 keys (got head_dim %d, %d keys)", hd, a.n_k);
+      return fail(PA_ERR_UNSUPPORTED, "attention core with relative_pos / top-k: needs 64-wide heads and at most 240 keys (got head_dim %d, %d keys)", hd, a.n_k);
     return launch_attn_single_slot(plan, st);
   }
   // 64-wide heads, one key block, staged output: two single-slot CTAs per SM (pa_cosched.cuh's attention role as a kernel)
@@ -536,7 +537,7 @@ int launch_attn_single_slot_t(const AttnPlan& plan, cudaStream_t st) {
   return PA_OK;
 }
 int launch_attn_single_slot(const AttnPlan& plan, cudaStream_t st) {
-  return plan.p.rel_pos ? launch_attn_single_slot_t<true>(plan, st) : launch_attn_single_slot_t<false>(plan, st);
+  return (plan.p.rel_pos || plan.p.row_thresh) ? launch_attn_single_slot_t<true>(plan, st) : launch_attn_single_slot_t<false>(plan, st);
 }
 
 // attention core + output projection in one kernel (pa_attn_proj.cuh): 64-wide heads, at most 64 keys, 128 <= C <= 512, 16-bit y
@@ -834,7 +835,8 @@ static int vit_check(const pa_vit_args* a) {
   return PA_OK;
 }
 
-static int vit_three_launches(const pa_vit_args* a, const void* x_in, int x_dtype, const void* residual, void* qkv, void* obuf, cudaStream_t st);
+static int vit_three_launches(const pa_vit_args* a, const void* x_in, int x_dtype, const void* residual, void* qkv, void* obuf, cudaStream_t st,
+                              float* knn_thresh = nullptr);
 
 // dependency counters (per 128-row tile of qkv + per image) followed by the co-scheduled kernel's scheduling words
 static size_t vit_counter_ints(const pa_vit_args* a) {
@@ -845,7 +847,8 @@ static size_t vit_counter_ints(const pa_vit_args* a) {
 size_t pa_vit_workspace_bytes(const pa_vit_args* a) {
   if (vit_check(a)) return 0;
   const size_t rows = (size_t)a->B * a->N;
-  return align_up(rows * 3 * a->C * 2, 1024) + align_up(rows * a->C * 2, 1024) + align_up(vit_counter_ints(a) * 4, 1024) + 1024;
+  return align_up(rows * 3 * a->C * 2, 1024) + align_up(rows * a->C * 2, 1024) + align_up(vit_counter_ints(a) * 4, 1024) +
+         (a->topk > 0 ? align_up(rows * a->H * 4, 1024) : 0) + 1024;
 }
 
 int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, void* stream) {
@@ -867,9 +870,17 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
   //      GEMMs under the softmax chain, two role-specialised CTAs per SM), else the sequenced kernel (pa_fused.cuh: the three
   //      phases back to back per SM).  PA_VIT_FUSED=0 selects three launches, =1 makes a shape no single-launch kernel
   //      takes an error instead of a silent switch; PA_VIT_COSCHED=0 / 1 never / always takes the co-scheduled kernel.
+  const int hd = C / a->H;
+  if (a->topk != 0) {
+    // kvt.KNNAttention (kvt.py:67-94): qkv GEMM -> per-row k-th largest score -> attention core with the row threshold -> proj GEMM
+    if (a->topk < 0 || a->topk > a->N) return fail(PA_ERR_BAD_SHAPE, "pa_vit_fwd: topk=%d must lie in [1, N=%d] (torch.topk, kvt.py:85)", a->topk, a->N);
+    if (hd != 64 || a->N > 240) return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(topk): needs 64-wide heads and N <= 240 (got head_dim %d, N=%d)", hd, a->N);
+    if ((rc = current_device_check())) return rc;
+    float* thr = reinterpret_cast<float*>(ws.take((size_t)rows * a->H * 4));
+    return vit_three_launches(a, a->x, a->dtype, nullptr, qkv, obuf, st, thr);
+  }
   const bool fused_forced = ev.vit_fused > 0 || ev.vit_cosched > 0;
   const bool fused_wanted = ev.vit_fused != 0;
-  const int hd = C / a->H;
   bool fused_ok = fused_wanted && a->N <= 256 && hd == 64;
   if (fused_forced && !fused_ok)
     return fail(PA_ERR_UNSUPPORTED, "pa_vit_fwd(single launch): needs N <= 256 (one key block) and 64-wide heads; got N=%d, head_dim=%d", a->N, hd);
@@ -1043,7 +1054,8 @@ int pa_vit_fwd(const pa_vit_args* a, void* workspace, size_t workspace_bytes, vo
 
 // qkv GEMM -> attention core -> proj GEMM (+ residual in its epilogue).  x_in: the qkv GEMM's A operand (a->x, or the LayerNorm
 // output of the block entry point); residual: nullptr or the tensor added to proj's result (dtype a->dtype, pitch C).
-static int vit_three_launches(const pa_vit_args* a, const void* x_in, int x_dtype, const void* residual, void* qkv, void* obuf, cudaStream_t st) {
+static int vit_three_launches(const pa_vit_args* a, const void* x_in, int x_dtype, const void* residual, void* qkv, void* obuf, cudaStream_t st,
+                              float* knn_thresh) {
   int rc;
   const long long rows = (long long)a->B * a->N;
   const int C = a->C, hd = C / a->H;
@@ -1056,6 +1068,17 @@ static int vit_three_launches(const pa_vit_args* a, const void* x_in, int x_dtyp
   at.k = qkv; at.v = qkv; at.ldk = 3 * C; at.k_group = (long long)a->N * 3 * C; at.k_col0 = C; at.v_col0 = 2 * C;
   at.o = obuf; at.ldo = C; at.o_group = (long long)a->N * C; at.o_col0 = 0;
   at.scale = a->scale;
+  if (knn_thresh != nullptr) {
+    // kvt.py:84-87: the k-th largest raw score of every row (scale > 0 keeps the order)
+    KnnParams kp;
+    kp.qkv = qkv; kp.thresh = knn_thresh; kp.G = a->B; kp.H = a->H; kp.N = a->N; kp.hd = hd; kp.topk = a->topk;
+    kp.ld = 3 * C; kp.group = (long long)a->N * 3 * C; kp.q_col0 = 0; kp.k_col0 = C;
+    const long long warps = rows * a->H;
+    knn_threshold_kernel<8><<<(int)((warps * 32 + 255) / 256), 256, 0, st>>>(kp);      // N <= 240 < 256 keys
+    PA_CUDA_OK(cudaGetLastError());
+    launch_counter()++;
+    at.row_thresh = knn_thresh;
+  }
   if ((rc = attn_launch(at, st))) return rc;
   // 3. y = O Wproj^T + b (+ residual)          (ViT.py:87, :116)
   return linear(obuf, PA_DTYPE_F16, C, a->proj_weight, PA_DTYPE_F16, a->proj_bias, a->y, a->out_dtype, C, rows, C, C, st,

@@ -57,6 +57,9 @@ struct AttnParams {
   // Single-slot kernel only.  rel_mul = 1 / scale, so that (s + r * rel_mul) * scale == s * scale + r.
   const float* rel_pos;
   float rel_mul;
+  // per-row score threshold (kvt.KNNAttention, kvt.py:84-87: only the top-k scores of a row take part in the softmax): raw
+  // (unscaled) scores below row_thresh[(g * H + h) * n_q + row] count as -inf.  fp32 [G, H, n_q], or nullptr.  Single-slot kernel only.
+  const float* row_thresh;
 };
 
 #define ATTN_TRACE(seq, slot_) do { if (p.trace != nullptr && blockIdx.x == 0 && (seq) < 32) p.trace[(seq) * 16 + (slot_)] = clock64(); } while (0)

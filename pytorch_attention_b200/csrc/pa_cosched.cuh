@@ -509,12 +509,18 @@ __device__ __forceinline__ void cs_attn_role(const CUtensorMap& tmQ, const CUten
       // attention of a config-3-sized CMT forward took 565 us instead of 69)
       const float* rp = nullptr;
       float rb0[16], rb1[16];
+      float thr = -INFINITY;                  // kvt.KNNAttention: raw scores below the row's k-th largest are masked
       const bool rel_pre = RELPOS && nst <= 2;
       if constexpr (RELPOS) {
-        const int h = (u / p.q_tiles) % p.H;
+        const int gh = u / p.q_tiles, h = gh % p.H;
         const int row = min(qt * 128 + trow, p.n_q - 1);
-        rp = p.rel_pos + ((size_t)h * p.n_q + row) * p.n_k + c_lo;
-        if (rel_pre && warp_active) {
+        if (p.row_thresh != nullptr) thr = __ldg(p.row_thresh + (size_t)gh * p.n_q + row);
+        if (p.rel_pos == nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { rb0[i] = 0.f; rb1[i] = 0.f; }
+        }
+        rp = p.rel_pos != nullptr ? p.rel_pos + ((size_t)h * p.n_q + row) * p.n_k + c_lo : nullptr;
+        if (rp != nullptr && rel_pre && warp_active) {
           if ((p.n_k & 3) == 0) {                    // rows 16-byte aligned (c_lo is a multiple of 16 columns)
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
@@ -548,20 +554,21 @@ __device__ __forceinline__ void cs_attn_role(const CUtensorMap& tmQ, const CUten
             tmem_ld16(t_my + k * 16, v);
             if (rel_pre) {
               tmem_ld_wait();
-              if (k == 0) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + rb0[i]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + rb1[i]);
+              for (int i = 0; i < 16; ++i) {
+                const float sv = __uint_as_float(v[i]);
+                v[i] = __float_as_uint(sv >= thr ? sv + (k == 0 ? rb0[i] : rb1[i]) : -INFINITY);
               }
             } else {
               float r[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) r[i] = (i < nv) ? __ldg(rp + k * 16 + i) * p.rel_mul : 0.f;
+              for (int i = 0; i < 16; ++i) r[i] = (rp != nullptr && i < nv) ? __ldg(rp + k * 16 + i) * p.rel_mul : 0.f;
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + r[i]);
+              for (int i = 0; i < 16; ++i) {
+                const float sv = __uint_as_float(v[i]);
+                v[i] = __float_as_uint(sv >= thr ? sv + r[i] : -INFINITY);
+              }
             }
             mx = chunk_max<16>(v, nv, mx);
           }
@@ -604,21 +611,22 @@ __device__ __forceinline__ void cs_attn_role(const CUtensorMap& tmQ, const CUten
           if constexpr (RELPOS) {
             if (rel_pre) {
               tmem_ld_wait();
-              if (k == 0) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) + rb0[i]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) + rb1[i]);
+              for (int i = 0; i < 16; ++i) {
+                const float sv = __uint_as_float(va[i]);
+                va[i] = __float_as_uint(sv >= thr ? sv + (k == 0 ? rb0[i] : rb1[i]) : -INFINITY);
               }
             } else {
               float r[16];
               const int nv = nvalid - k * 16;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) r[i] = (i < nv) ? __ldg(rp + k * 16 + i) * p.rel_mul : 0.f;
+              for (int i = 0; i < 16; ++i) r[i] = (rp != nullptr && i < nv) ? __ldg(rp + k * 16 + i) * p.rel_mul : 0.f;
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) + r[i]);
+              for (int i = 0; i < 16; ++i) {
+                const float sv = __uint_as_float(va[i]);
+                va[i] = __float_as_uint(sv >= thr ? sv + r[i] : -INFINITY);
+              }
             }
           } else {
             tmem_ld_wait();
@@ -791,7 +799,8 @@ vit_cosched_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
 
 // The attention role as a kernel of its own (no GEMM role, no dependency counters): two single-slot CTAs per SM instead of the
 // two-slot CTA of attn_core_kernel.  Used for 64-wide heads with a single key block (ViT / PVT / CvT three-launch paths).
-// RELPOS: an additive fp32 score bias [H, n_q, n_k] before the softmax (cmt.Attention, cmt.py:100).
+// RELPOS: the score-modifying variant -- an additive fp32 score bias [H, n_q, n_k] before the softmax (cmt.Attention, cmt.py:100)
+// and / or a per-row threshold below which scores are masked (kvt.KNNAttention, kvt.py:84-87).
 template <bool RELPOS>
 __global__ void __launch_bounds__(CS_THREADS, 2)
 attn_single_slot_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,

@@ -166,6 +166,78 @@ __global__ void p2t_tokens_kernel(const P2tTokParams p) {
     orow[c] = __float2half_rn(fmaf((p2t_token_value(p, base, l, pi, pj, c) - mean) * rstd, __ldg(p.gamma + c), __ldg(p.beta + c)));
 }
 
+// kvt.KNNAttention (kvt.py:84-87): per query row the k-th largest raw score q.k -- the threshold below which the attention kernel
+// masks scores.  One warp per (image, head, row): lane l holds the scores of keys l, l+32, ... (fp32 dot products of the fp16
+// q / k rows in the qkv buffer), then an exact radix select over the order-preserving integer image of the floats: 32 rounds of
+// "how many scores are >= candidate" (per-lane count + warp sum).  SIMT on purpose: 2 N hd flops per row are nothing next to the
+// projections, and the selection is integer work.  A row whose k-th and (k+1)-th scores differ by less than fp32 rounding may keep
+// k-1 or k+1 entries (as two PyTorch backends may).
+struct KnnParams {
+  const void* qkv;                 // fp16 [G, N, ld]: q at column q_col0 + h*hd, k at k_col0 + h*hd
+  float* thresh;                   // [G, H, N]
+  int G, H, N, hd, topk;
+  long long ld, group;             // row / group pitch in elements
+  int q_col0, k_col0;
+};
+template <int MAXK>                // keys per lane: N <= 32 * MAXK
+__global__ void knn_threshold_kernel(const KnnParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long long)p.G * p.H * p.N) return;
+  const int row = (int)(wid % p.N);
+  const int h = (int)((wid / p.N) % p.H);
+  const int g = (int)(wid / ((long long)p.N * p.H));
+  const __half* base = reinterpret_cast<const __half*>(p.qkv) + (long long)g * p.group;
+  const __half* qr = base + (long long)row * p.ld + p.q_col0 + h * p.hd;
+  uint32_t key[MAXK];
+#pragma unroll
+  for (int j = 0; j < MAXK; ++j) {
+    const int kidx = lane + 32 * j;
+    float s = 0.f;
+    if (kidx < p.N) {
+      const __half* kr = base + (long long)kidx * p.ld + p.k_col0 + h * p.hd;
+      for (int d = 0; d < p.hd; d += 8) {
+        const uint4 qa = __ldg(reinterpret_cast<const uint4*>(qr + d)), ka = __ldg(reinterpret_cast<const uint4*>(kr + d));
+        const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
+        const __half2* k2 = reinterpret_cast<const __half2*>(&ka);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = __half22float2(q2[i]), b = __half22float2(k2[i]);
+          s = fmaf(a.x, b.x, s);
+          s = fmaf(a.y, b.y, s);
+        }
+      }
+      uint32_t u = __float_as_uint(s);
+      key[j] = u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);       // ascending unsigned order == ascending float order
+    } else {
+      key[j] = 0u;                                                   // below every real score
+    }
+  }
+  uint32_t res = 0u;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = res | (1u << bit);
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) cnt += (key[j] >= cand) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (cnt >= p.topk) res = cand;                                   // at least k scores are >= cand: the k-th largest is too
+  }
+  // The attention kernel's tensor-core scores accumulate in another order than the dot products above: compared against the k-th
+  // largest value ITSELF, the k-th entry would fall below its own threshold in half of the rows (measured: 46 % of the rows kept
+  // k - 1 entries).  The threshold handed over is the midpoint between the k-th largest score and the next smaller one.
+  uint32_t lower = 0u;                                               // largest key below res; 0 = none (real keys are never 0)
+#pragma unroll
+  for (int j = 0; j < MAXK; ++j) lower = (key[j] < res && key[j] > lower) ? key[j] : lower;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { const uint32_t other = __shfl_xor_sync(0xffffffffu, lower, o); lower = other > lower ? other : lower; }
+  if (lane == 0) {
+    const float kth = __uint_as_float(res ^ ((res >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+    const float nxt = __uint_as_float(lower ^ ((lower >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+    p.thresh[wid] = lower != 0u ? 0.5f * (kth + nxt) : -INFINITY;    // topk == N: every score is kept
+  }
+}
+
 // SegFormer spatial reduction (segformer.py:27, 38-39): a DENSE conv with k = stride = sr is a GEMM over non-overlapping
 // patches.  This kernel lays the patches out as that GEMM's K-major A operand -- a pure re-partition of x (kernel == stride:
 // every element of x moves exactly once):  out[b, i*Ws+j, (u*sr+v)*C + c] = x[b, (sr*i+u)*W + sr*j+v, c]

@@ -52,6 +52,7 @@ class Attention(StagedModule):
         a.scale = float(self.scale)
         a.x, a.qkv_weight, a.qkv_bias = ops._ptr(x), ops._ptr(wq), ops._ptr(bq)
         a.proj_weight, a.proj_bias, a.y = ops._ptr(wp), ops._ptr(bp), ops._ptr(y)
+        a.topk = int(getattr(self, "topk", 0) or 0)      # kvt.KNNAttention sets it (kvt.py:68); 0 = plain softmax
         lib = L.load()
         with torch.cuda.device(x.device):
             need = lib.pa_vit_workspace_bytes(ctypes.byref(a))

@@ -37,7 +37,7 @@ def rel_max(y, ref):
 def dropin_class(variant):
     import pytorch_attention_b200 as pa
     return {"vit": pa.vit.Attention, "vit_block": pa.vit.TransformerEncoder, "setr": pa.setr.Attention, "moat": pa.moat.Attention,
-            "bvit": pa.bvit.Broad_Attention, "dilateformer": pa.dilateformer.GlobalAttention, "p2t": pa.p2t.PoolingAttention, "pvt": pa.pvt.Attention, "pvt_block": pa.pvt.Block, "segformer": pa.segformer.Attention, "cmt": pa.cmt.Attention,
+            "bvit": pa.bvit.Broad_Attention, "dilateformer": pa.dilateformer.GlobalAttention, "p2t": pa.p2t.PoolingAttention, "kvt": pa.kvt.KNNAttention, "pvt": pa.pvt.Attention, "pvt_block": pa.pvt.Block, "segformer": pa.segformer.Attention, "cmt": pa.cmt.Attention,
             "cvt": pa.cvt.Attention, "lepe": pa.cswin.LePEAttention, "cswin_block": pa.cswin.CSWinBlock, "xca": pa.xcit.XCA,
             "xca_block": pa.xcit.XCABlockAttentionHalf, "pam": pa.dual_attention.PAM, "class_attn": pa.xcit.ClassAttention}[variant]
 

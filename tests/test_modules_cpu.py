@@ -220,3 +220,14 @@ def test_p2t_pooling_attention_matches_live_reference_contract():
     assert {k: v.shape for k, v in r.state_dict().items()} == {k: v.shape for k, v in m.state_dict().items()}
     m.load_state_dict(r.state_dict())
     assert m.num_elements == r.num_elements
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference not mounted")
+def test_kvt_knn_attention_matches_live_reference_contract():
+    ref = _ref("kvt").KNNAttention
+    ours = pa.kvt.KNNAttention
+    assert str(inspect.signature(ref.__init__)) == str(inspect.signature(ours.__init__))
+    r, m = ref(128, 2, qkv_bias=True, topk=50), ours(128, 2, qkv_bias=True, topk=50)
+    assert {k: v.shape for k, v in r.state_dict().items()} == {k: v.shape for k, v in m.state_dict().items()}
+    m.load_state_dict(r.state_dict())
+    assert m.topk == r.topk == 50
