@@ -95,3 +95,56 @@ def test_python_error_mapping():
         L.check(L.PA_ERR_UNSUPPORTED)
     with pytest.raises(L.PaError):
         L.check(L.PA_ERR_CUDA)
+
+
+def test_round2_entry_points_validate_arguments_without_gpu():
+    """The sibling / block entry points of round 2 reject bad arguments before anything touches a device."""
+    lib = L.load()
+    # pa_pvt_fwd: segformer's dense reduction mode, cmt's relative_pos, p2t's external key tokens
+    p = L.PvtArgs()
+    p.B, p.N, p.C, p.H, p.Himg, p.Wimg, p.sr = 1, 64, 128, 2, 8, 8, 2
+    p.sr_mode = 3
+    assert lib.pa_pvt_workspace_bytes(C.byref(p)) == 0
+    assert lib.pa_pvt_fwd(C.byref(p), None, 0, None) == L.PA_ERR_BAD_SHAPE
+    p.sr_mode, p.Himg, p.Wimg, p.N = 1, 9, 9, 81
+    assert lib.pa_pvt_fwd(C.byref(p), None, 0, None) == L.PA_ERR_BAD_SHAPE          # 9 % sr_ratio 2
+    p.Himg, p.Wimg, p.N = 8, 8, 64
+    dense = lib.pa_pvt_workspace_bytes(C.byref(p))
+    p.sr_mode = 0
+    assert dense > lib.pa_pvt_workspace_bytes(C.byref(p)) > 0                        # the patch matrix of the dense reduction
+    p.kv_tokens, p.kv_count = 16, 10                                                 # external key tokens need sr == 1
+    assert lib.pa_pvt_fwd(C.byref(p), None, 0, None) == L.PA_ERR_BAD_SHAPE
+    blk = L.PvtBlockArgs()
+    assert lib.pa_pvt_block_attn_workspace_bytes(C.byref(blk)) == 0
+    assert lib.pa_pvt_block_attn_fwd(None, None, 0, None) == L.PA_ERR_NULL
+    # pa_p2t_fwd: pyramid levels
+    t = L.P2tArgs()
+    t.attn.B, t.attn.N, t.attn.C, t.attn.H, t.attn.Himg, t.attn.Wimg, t.attn.sr = 1, 196, 128, 2, 14, 14, 1
+    t.n_levels = 5
+    assert lib.pa_p2t_workspace_bytes(C.byref(t)) == 0
+    assert lib.pa_p2t_fwd(C.byref(t), None, 0, None) == L.PA_ERR_BAD_SHAPE
+    t.n_levels = 2
+    t.pool_h[0], t.pool_w[0], t.pool_h[1], t.pool_w[1] = 14, 14, 20, 2
+    assert lib.pa_p2t_fwd(C.byref(t), None, 0, None) == L.PA_ERR_BAD_SHAPE          # pooled size 20 > H = 14
+    t.pool_h[1] = 7
+    assert lib.pa_p2t_workspace_bytes(C.byref(t)) > 0
+    # pa_bvit_fwd: no output projection only when the inner width equals dim and y is fp16
+    b = L.BvitArgs()
+    b.B, b.N, b.C, b.H, b.dim_head = 1, 50, 64, 2, 64
+    assert lib.pa_bvit_fwd(C.byref(b), None, 0, None) == L.PA_ERR_UNSUPPORTED
+    b.H = 1
+    assert lib.pa_bvit_workspace_bytes(C.byref(b)) > 0
+    b.dim_head = 24
+    assert lib.pa_bvit_fwd(C.byref(b), None, 0, None) == L.PA_ERR_UNSUPPORTED       # not a multiple of 16
+    # pa_xca_block_attn_fwd
+    xb = L.XcaBlockArgs()
+    assert lib.pa_xca_block_attn_workspace_bytes(C.byref(xb)) == 0
+    xb.attn.B, xb.attn.N, xb.attn.C, xb.attn.H = 1, 196, 128, 4
+    assert lib.pa_xca_block_attn_workspace_bytes(C.byref(xb)) > 0
+    assert lib.pa_xca_block_attn_fwd(C.byref(xb), None, 0, None) == L.PA_ERR_NULL
+    # pa_vit_fwd(topk): the workspace grows by the per-row thresholds
+    v = L.VitArgs()
+    v.B, v.N, v.C, v.H = 2, 197, 768, 12
+    plain = lib.pa_vit_workspace_bytes(C.byref(v))
+    v.topk = 100
+    assert lib.pa_vit_workspace_bytes(C.byref(v)) >= plain + 2 * 197 * 12 * 4
